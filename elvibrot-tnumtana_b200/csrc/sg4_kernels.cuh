@@ -1,0 +1,244 @@
+// sg4_kernels.cuh -- sm_100a kernels of the SG4 H|psi> action.
+//
+// One CTA processes one Smolyak term at a time (persistent grid, terms sorted by
+// cost): gather -> mode-by-mode B->G -> sum_iterm F_iterm(Q) d^(i,j) on the term grid
+// -> mode-by-mode G->B -> weighted scatter-add.  The whole term lives in shared memory
+// between the gather and the scatter; HBM sees only the packed psi / Hpsi vectors, the
+// int32 mapping slice and the operator grids (SURVEY.md 8d "algorithmic bytes").
+//
+// Reference routines fused here (reference tree, file:line):
+//   tabPackedBasis_TO_tabR_AT_iG        sub_Basis_SG4/sub_module_basis_BtoG_GtoB_SG4.f90:1176-1246
+//   BDP_TO_GDP_OF_SmolyakRep            ...:2385-2496
+//   sub_TabOpPsi_OF_ONEDP_FOR_SGtype4   sub_Operator/sub_OpPsi_SG4.f90:1354-1546 (type_Op 0 and 1)
+//   DerivOp_TO_RDP_OF_SmolaykRep        ...BtoG_GtoB_SG4.f90:2690-2795
+//   GDP_TO_BDP_OF_SmolyakRep            ...:2497-2581
+//   tabR_AT_iG_TO_tabPackedBasis        ...:1250-1289
+#pragma once
+#include <cstdint>
+#include "sg4_internal.h"
+
+namespace evr {
+
+// ---- device-side plan -------------------------------------------------------------
+struct TermDev {                 // one per Smolyak term of this plan's range (work order)
+    long long map_off;           // start of the term's slice in d_map
+    long long grid_off;          // start of the term's slice in every operator grid
+    double    weight;            // WeightSG(iG)
+    int       nbT, nq;           // prod nb_k, prod nq_k
+    int       lev_off;           // start of the term's D levels in d_lev
+    int       pad;
+};
+
+struct OpTermDev {               // one per live (not grid_zero) operator term
+    int m1, m2;                  // 0-based SG4 modes of the derivative, -1 = none (m1<=m2 if both)
+    int grid_slot;               // >=0: index of the variable grid; -1: constant (Mat_cte)
+    int pad;
+    double cte[EVR_MAXCH * EVR_MAXCH];   // cte[i + nb0*j] = Mat_cte(i,j)
+};
+
+struct PlanDev {
+    int D, LG, nb0, n_terms;     // n_terms = terms in this plan's range
+    long long nb;                // packed basis size per channel
+    long long NQ_local;          // grid points of the range (= stride between grid blocks)
+    int n_opterms, n_var;
+    int cap;                     // doubles per shared-memory buffer
+    int type_Op;
+    const TermDev   *terms;      // [n_terms], work order
+    const uint8_t   *lev;        // [n_terms*D]
+    const int32_t   *map;        // [S_local]
+    const int32_t   *nq_of;      // [D*(LG+1)]
+    const int32_t   *nb_of;
+    const int32_t   *offB;       // [D*(LG+1)] offsets into B/BTw pools
+    const int32_t   *offG;       // [D*(LG+1)] offsets into D1/D2 pools
+    const double    *B, *BTw, *D1, *D2;
+    const OpTermDev *opterms;    // [n_opterms]
+    const double    *grids;      // [n_var][nb0*nb0][NQ_local]  (slot-major; (i + nb0*j)-major; point)
+};
+
+// ---- generic one-mode product through shared memory ----------------------------------
+//   out[a + left*(q + n_out*c)] = sum_b M[q + n_out*b] * in[a + left*(b + n_in*c)]
+//   a < left, c < right (right already includes the channel count), M in global (L1-resident).
+__device__ __forceinline__ void mode_product(const double *__restrict__ M, int n_out, int n_in,
+                                             const double *in, double *out, int left, int right)
+{
+    const int total = left * n_out * right;
+    const int lo = left * n_out;
+    for (int o = threadIdx.x; o < total; o += blockDim.x) {
+        const int c = o / lo;
+        const int r = o - c * lo;
+        const int q = r / left;
+        const int a = r - q * left;
+        const double *x = in + a + left * n_in * c;
+        double s = 0.0;
+        for (int b = 0; b < n_in; ++b) s = fma(__ldg(M + q + n_out * b), x[left * b], s);
+        out[o] = s;
+    }
+}
+
+// ---- generic term kernel (any type_Op 0/1 term list, any mode sizes that fit) ----------
+// dynamic smem: [2*cap doubles][ints: nq_of,nb_of,offB,offG (4*D*(LG+1))][per-term ints 5*D]
+__global__ void __launch_bounds__(256)
+sg4_term_kernel_generic(const PlanDev P, const int npsi,
+                        const double *__restrict__ psi, double *__restrict__ Hpsi)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double *bufA = reinterpret_cast<double *>(smem_raw);
+    double *bufB = bufA + P.cap;
+    int *s_nq_of = reinterpret_cast<int *>(bufB + P.cap);
+    const int nT = P.D * (P.LG + 1);
+    int *s_nb_of = s_nq_of + nT;
+    int *s_offB  = s_nb_of + nT;
+    int *s_offG  = s_offB + nT;
+    int *s_tnq   = s_offG + nT;        // per-term: nq_k
+    int *s_tnb   = s_tnq + P.D;        //           nb_k
+    int *s_oB    = s_tnb + P.D;        //           table offsets for (k,l_k)
+    int *s_oG    = s_oB + P.D;
+    int *s_str   = s_oG + P.D;         //           grid stride of mode k (first mode fastest)
+
+    for (int i = threadIdx.x; i < nT; i += blockDim.x) {
+        s_nq_of[i] = P.nq_of[i]; s_nb_of[i] = P.nb_of[i];
+        s_offB[i] = P.offB[i];   s_offG[i] = P.offG[i];
+    }
+    __syncthreads();
+
+    const int D = P.D, nb0 = P.nb0;
+    const long long nvec = P.nb * nb0;
+
+    for (int it = blockIdx.x; it < P.n_terms; it += gridDim.x) {
+        const TermDev T = P.terms[it];
+        const uint8_t *lev = P.lev + T.lev_off;
+        __syncthreads();               // previous term fully done before the per-term tables change
+        if (threadIdx.x == 0) {
+            int str = 1;
+            for (int k = 0; k < D; ++k) {
+                const int i = k * (P.LG + 1) + lev[k];
+                s_tnq[k] = s_nq_of[i]; s_tnb[k] = s_nb_of[i];
+                s_oB[k] = s_offB[i];   s_oG[k] = s_offG[i];
+                s_str[k] = str; str *= s_nq_of[i];
+            }
+        }
+        __syncthreads();
+        const int nq = T.nq, nbT = T.nbT;
+        const int32_t *mp = P.map + T.map_off;
+
+        for (int ip = 0; ip < npsi; ++ip) {
+            const double *x = psi + (long long)ip * nvec;
+            double *y = Hpsi + (long long)ip * nvec;
+            // ---- gather
+            for (int j = threadIdx.x; j < nbT; j += blockDim.x) {
+                const int m = mp[j];
+                for (int c = 0; c < nb0; ++c)
+                    bufA[c * nbT + j] = (m > 0) ? __ldg(x + (long long)c * P.nb + (m - 1)) : 0.0;
+            }
+            __syncthreads();
+            double *cur = bufA, *oth = bufB;
+            // ---- B -> G, mode 1 first
+            {
+                int left = 1, right = nbT * nb0;
+                for (int k = 0; k < D; ++k) {
+                    const int nbk = s_tnb[k], nqk = s_tnq[k];
+                    right /= nbk;
+                    if (nbk == 1 && nqk == 1) {
+                        const double s = __ldg(P.B + s_oB[k]);
+                        const int total = left * right;
+                        for (int o = threadIdx.x; o < total; o += blockDim.x) cur[o] *= s;
+                    } else {
+                        mode_product(P.B + s_oB[k], nqk, nbk, cur, oth, left, right);
+                        double *t = cur; cur = oth; oth = t;
+                    }
+                    left *= nqk;
+                    __syncthreads();
+                }
+            }
+            // ---- operator on the term grid: oth(q,i) = sum_iterm sum_j F(q,i,j) [d psi](q,j)
+            for (int q = threadIdx.x; q < nq; q += blockDim.x) {
+                double acc[EVR_MAXCH];
+#pragma unroll
+                for (int i = 0; i < EVR_MAXCH; ++i) acc[i] = 0.0;
+                for (int t = 0; t < P.n_opterms; ++t) {
+                    const OpTermDev &O = P.opterms[t];
+                    double d[EVR_MAXCH];
+                    const int m1 = O.m1, m2 = O.m2;
+                    if (m1 < 0 && m2 < 0) {
+#pragma unroll
+                        for (int j = 0; j < EVR_MAXCH; ++j) if (j < nb0) d[j] = cur[j * nq + q];
+                    } else if (m1 < 0 || m2 < 0 || m1 == m2) {
+                        const int k = (m1 >= 0) ? m1 : m2;
+                        const double *M = ((m1 == m2) ? P.D2 : P.D1) + s_oG[k];
+                        const int n = s_tnq[k], st = s_str[k];
+                        const int qk = (q / st) % n;
+                        const int base = q - qk * st;
+#pragma unroll
+                        for (int j = 0; j < EVR_MAXCH; ++j) if (j < nb0) {
+                            double s = 0.0;
+                            for (int b = 0; b < n; ++b) s = fma(__ldg(M + qk + n * b), cur[j * nq + base + b * st], s);
+                            d[j] = s;
+                        }
+                    } else {
+                        const double *Ma = P.D1 + s_oG[m1], *Mb = P.D1 + s_oG[m2];
+                        const int na = s_tnq[m1], sa = s_str[m1], nbb = s_tnq[m2], sb = s_str[m2];
+                        const int qa = (q / sa) % na, qb = (q / sb) % nbb;
+                        const int base = q - qa * sa - qb * sb;
+#pragma unroll
+                        for (int j = 0; j < EVR_MAXCH; ++j) if (j < nb0) {
+                            double s = 0.0;
+                            for (int b2 = 0; b2 < nbb; ++b2) {
+                                double s1 = 0.0;
+                                for (int b1 = 0; b1 < na; ++b1)
+                                    s1 = fma(__ldg(Ma + qa + na * b1), cur[j * nq + base + b1 * sa + b2 * sb], s1);
+                                s = fma(__ldg(Mb + qb + nbb * b2), s1, s);
+                            }
+                            d[j] = s;
+                        }
+                    }
+                    if (O.grid_slot < 0) {
+#pragma unroll
+                        for (int i = 0; i < EVR_MAXCH; ++i) if (i < nb0)
+#pragma unroll
+                            for (int j = 0; j < EVR_MAXCH; ++j) if (j < nb0)
+                                acc[i] = fma(O.cte[i + nb0 * j], d[j], acc[i]);
+                    } else {
+                        const double *g = P.grids + ((long long)O.grid_slot * nb0 * nb0) * P.NQ_local + T.grid_off + q;
+#pragma unroll
+                        for (int i = 0; i < EVR_MAXCH; ++i) if (i < nb0)
+#pragma unroll
+                            for (int j = 0; j < EVR_MAXCH; ++j) if (j < nb0)
+                                acc[i] = fma(__ldg(g + (long long)(i + nb0 * j) * P.NQ_local), d[j], acc[i]);
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < EVR_MAXCH; ++i) if (i < nb0) oth[i * nq + q] = acc[i];
+            }
+            __syncthreads();
+            { double *t = cur; cur = oth; oth = t; }
+            // ---- G -> B
+            {
+                int left = 1, right = nq * nb0;
+                for (int k = 0; k < D; ++k) {
+                    const int nbk = s_tnb[k], nqk = s_tnq[k];
+                    right /= nqk;
+                    if (nbk == 1 && nqk == 1) {
+                        const double s = __ldg(P.BTw + s_oB[k]);
+                        const int total = left * right;
+                        for (int o = threadIdx.x; o < total; o += blockDim.x) cur[o] *= s;
+                    } else {
+                        mode_product(P.BTw + s_oB[k], nbk, nqk, cur, oth, left, right);
+                        double *t = cur; cur = oth; oth = t;
+                    }
+                    left *= nbk;
+                    __syncthreads();
+                }
+            }
+            // ---- weighted scatter-add
+            for (int j = threadIdx.x; j < nbT; j += blockDim.x) {
+                const int m = mp[j];
+                if (m > 0)
+                    for (int c = 0; c < nb0; ++c)
+                        atomicAdd(y + (long long)c * P.nb + (m - 1), T.weight * cur[c * nbT + j]);
+            }
+            __syncthreads();
+        }
+    }
+}
+
+} // namespace evr

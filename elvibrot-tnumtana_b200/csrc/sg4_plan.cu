@@ -1,0 +1,368 @@
+// sg4_plan.cu -- host side of the evr_sg4 C-ABI: plan construction (device-resident copy of
+// param_SGType2 / tab_basisPrimSG / OpGrid for a term range), launch logic, host<->device staging.
+//
+// Replaces the body of sub_TabOpPsi_FOR_SGtype4 (sub_Operator/sub_OpPsi_SG4.f90:678-979) and of
+// Action_MPI_S1 minus its reduce (sub_OpPsi_SG4_MPI.f90:454-571).  No CPU fallback exists: every
+// entry point fails with a message if CUDA is unavailable.
+#include "../../include/evr_sg4.h"
+#include "sg4_internal.h"
+#include "sg4_kernels.cuh"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <numeric>
+#include <string>
+#include <vector>
+
+namespace evr {
+static thread_local std::string g_err;
+int fail(const std::string &msg) { g_err = msg; return 1; }
+}
+using evr::fail;
+
+#define CUDA_TRY(expr)                                                                         \
+    do {                                                                                       \
+        cudaError_t e__ = (expr);                                                              \
+        if (e__ != cudaSuccess)                                                                \
+            return fail(std::string(#expr) + ": " + cudaGetErrorString(e__));                  \
+    } while (0)
+
+extern "C" int evr_sg4_version(void) { return 100; }
+extern "C" const char *evr_sg4_last_error(void) { return evr::g_err.c_str(); }
+
+struct evr_sg4_plan {
+    int device = 0;
+    int D = 0, nb_SG = 0, nb0 = 1, LG = 0;
+    int64_t nb = 0;
+    int iG_begin = 0, iG_end = 0, n_terms = 0;
+    int64_t S_local = 0, NQ_local = 0, NQ_total = 0;
+    int64_t grid_start = 0;                 // first grid point of the range in the full Smolyak grid
+    int cap = 0;                            // doubles per smem buffer (incl. nb0)
+    int sm_count = 0;
+    bool op_set = false;
+    int type_Op = 1, n_opterms = 0, n_var = 0;
+    int64_t launches = 0;
+    int64_t flops_npsi1 = 0;
+    // host copies needed later
+    std::vector<int32_t> h_tab_l, h_nq_of, h_nb_of, h_tab_nq, h_tab_nb;
+    std::vector<int> order;                 // work order -> local term index
+    // device
+    evr::TermDev *d_terms = nullptr;
+    uint8_t *d_lev = nullptr;
+    int32_t *d_map = nullptr, *d_nq_of = nullptr, *d_nb_of = nullptr, *d_offB = nullptr, *d_offG = nullptr;
+    double *d_B = nullptr, *d_BTw = nullptr, *d_D1 = nullptr, *d_D2 = nullptr;
+    evr::OpTermDev *d_opterms = nullptr;
+    double *d_grids = nullptr;
+    double *d_psi = nullptr, *d_Hpsi = nullptr;   // staging for the host-buffer entry point
+    int64_t stage_cap = 0;
+    cudaStream_t stream = nullptr;
+    size_t smem_bytes = 0;
+    int grid_ctas = 0;
+    evr::PlanDev pd{};
+};
+
+template <class T>
+static int upload(T **dptr, const T *h, size_t n)
+{
+    if (n == 0) n = 1;
+    CUDA_TRY(cudaMalloc((void **)dptr, n * sizeof(T)));
+    if (h) CUDA_TRY(cudaMemcpy(*dptr, h, n * sizeof(T), cudaMemcpyHostToDevice));
+    return 0;
+}
+
+extern "C" int evr_sg4_plan_create(evr_sg4_plan **out, int device,
+                                   int D, int nb_SG, int nb0, int64_t nb, int LG,
+                                   const int32_t *tab_l, const double *WeightSG,
+                                   const int32_t *tab_nq, const int32_t *tab_nb,
+                                   const int32_t *tab_iB,
+                                   const int32_t *nq_of, const int32_t *nb_of,
+                                   const double *B, const double *BTw, const double *D1, const double *D2,
+                                   int iG_begin, int iG_end)
+{
+    if (!out || !tab_l || !WeightSG || !tab_nq || !tab_nb || !tab_iB || !nq_of || !nb_of || !B || !BTw || !D1 || !D2)
+        return fail("evr_sg4_plan_create: null argument");
+    if (D < 1 || D > EVR_MAXD) return fail("evr_sg4_plan_create: D must be in [1," + std::to_string(EVR_MAXD) + "]");
+    if (nb0 < 1 || nb0 > EVR_MAXCH) return fail("evr_sg4_plan_create: nb0 must be in [1," + std::to_string(EVR_MAXCH) + "]");
+    if (LG < 0 || LG > 254) return fail("evr_sg4_plan_create: LG out of range");
+    if (nb_SG < 1 || nb < 1) return fail("evr_sg4_plan_create: empty basis");
+    if (iG_begin < 0 || iG_end > nb_SG || iG_begin > iG_end) return fail("evr_sg4_plan_create: bad term range");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1)
+        return fail("evr_sg4_plan_create: no CUDA device available (this library has no CPU fallback)");
+    if (device < 0) CUDA_TRY(cudaGetDevice(&device));
+    if (device >= ndev) return fail("evr_sg4_plan_create: device index out of range");
+    CUDA_TRY(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) return fail("evr_sg4_plan_create: built for sm_100a (Blackwell) only");
+
+    auto *p = new evr_sg4_plan();
+    p->device = device; p->D = D; p->nb_SG = nb_SG; p->nb0 = nb0; p->nb = nb; p->LG = LG;
+    p->iG_begin = iG_begin; p->iG_end = iG_end; p->n_terms = iG_end - iG_begin;
+    p->sm_count = prop.multiProcessorCount;
+    const int nT = D * (LG + 1);
+    p->h_nq_of.assign(nq_of, nq_of + nT);
+    p->h_nb_of.assign(nb_of, nb_of + nT);
+    p->h_tab_l.assign(tab_l, tab_l + (size_t)nb_SG * D);
+    p->h_tab_nq.assign(tab_nq, tab_nq + nb_SG);
+    p->h_tab_nb.assign(tab_nb, tab_nb + nb_SG);
+
+    // canonical table offsets
+    std::vector<int32_t> offB(nT), offG(nT);
+    int64_t ob = 0, og = 0;
+    for (int i = 0; i < nT; ++i) {
+        if (nq_of[i] < 1 || nb_of[i] < 1) { delete p; return fail("evr_sg4_plan_create: nq/nb < 1"); }
+        offB[i] = (int32_t)ob; offG[i] = (int32_t)og;
+        ob += (int64_t)nq_of[i] * nb_of[i];
+        og += (int64_t)nq_of[i] * nq_of[i];
+        if (ob >= ((int64_t)1 << 31) || og >= ((int64_t)1 << 31)) { delete p; return fail("evr_sg4_plan_create: 1-D tables too large"); }
+    }
+    // prefix sums over ALL terms (grid offsets refer to the full Smolyak grid)
+    std::vector<int64_t> pre_nq(nb_SG + 1, 0), pre_nb(nb_SG + 1, 0);
+    for (int iG = 0; iG < nb_SG; ++iG) {
+        int64_t nq = 1, nbT = 1;
+        for (int k = 0; k < D; ++k) {
+            int l = tab_l[(size_t)iG * D + k];
+            if (l < 0 || l > LG) { delete p; return fail("evr_sg4_plan_create: level out of range in tab_l"); }
+            nq *= nq_of[k * (LG + 1) + l]; nbT *= nb_of[k * (LG + 1) + l];
+        }
+        if (nq != tab_nq[iG] || nbT != tab_nb[iG]) { delete p; return fail("evr_sg4_plan_create: tab_nq/nb_OF_SRep inconsistent with tab_l"); }
+        pre_nq[iG + 1] = pre_nq[iG] + nq; pre_nb[iG + 1] = pre_nb[iG] + nbT;
+    }
+    p->NQ_total = pre_nq[nb_SG];
+    p->grid_start = pre_nq[iG_begin];
+    p->NQ_local = pre_nq[iG_end] - pre_nq[iG_begin];
+    p->S_local = pre_nb[iG_end] - pre_nb[iG_begin];
+    const int64_t map_start = pre_nb[iG_begin];
+    for (int64_t j = 0; j < p->S_local; ++j) {
+        int32_t m = tab_iB[map_start + j];
+        if (m < 0 || m > nb) { delete p; return fail("evr_sg4_plan_create: mapping entry out of range"); }
+    }
+
+    // per-term cost, capacity, work order
+    std::vector<double> cost(p->n_terms);
+    int64_t cap = 1, flops = 0;
+    for (int t = 0; t < p->n_terms; ++t) {
+        const int iG = iG_begin + t;
+        int64_t mx = 1, sumn = 0;
+        int64_t left = 1, right = tab_nb[iG];
+        for (int k = 0; k < D; ++k) {
+            int l = tab_l[(size_t)iG * D + k];
+            int a = nq_of[k * (LG + 1) + l], b = nb_of[k * (LG + 1) + l];
+            mx *= std::max(a, b);
+            sumn += a + b;
+            right /= b;
+            flops += 2 * 2 * left * a * b * right;       // B->G and G->B (same count)
+            left *= a;
+        }
+        cap = std::max(cap, mx);
+        cost[t] = (double)tab_nq[iG] * (double)sumn;
+    }
+    p->flops_npsi1 = flops * nb0;
+    if (cap * nb0 * 2 * (int64_t)sizeof(double) > 220 * 1024) {
+        delete p;
+        return fail("evr_sg4_plan_create: a Smolyak term does not fit in shared memory (max term size*nb0 = " +
+                    std::to_string(cap * nb0) + " doubles)");
+    }
+    p->cap = (int)(cap * nb0);
+    p->order.resize(p->n_terms);
+    std::iota(p->order.begin(), p->order.end(), 0);
+    std::stable_sort(p->order.begin(), p->order.end(), [&](int a, int b) { return cost[a] > cost[b]; });
+
+    std::vector<evr::TermDev> terms(p->n_terms);
+    std::vector<uint8_t> lev((size_t)p->n_terms * D);
+    for (int w = 0; w < p->n_terms; ++w) {
+        const int t = p->order[w], iG = iG_begin + t;
+        evr::TermDev &T = terms[w];
+        T.map_off = pre_nb[iG] - map_start;
+        T.grid_off = pre_nq[iG] - p->grid_start;
+        T.weight = WeightSG[iG];
+        T.nbT = tab_nb[iG]; T.nq = tab_nq[iG];
+        T.lev_off = w * D; T.pad = 0;
+        for (int k = 0; k < D; ++k) lev[(size_t)w * D + k] = (uint8_t)tab_l[(size_t)iG * D + k];
+    }
+    int rc = 0;
+    rc |= upload(&p->d_terms, terms.data(), terms.size());
+    rc |= upload(&p->d_lev, lev.data(), lev.size());
+    rc |= upload(&p->d_map, tab_iB + map_start, (size_t)p->S_local);
+    rc |= upload(&p->d_nq_of, nq_of, (size_t)nT);
+    rc |= upload(&p->d_nb_of, nb_of, (size_t)nT);
+    rc |= upload(&p->d_offB, offB.data(), (size_t)nT);
+    rc |= upload(&p->d_offG, offG.data(), (size_t)nT);
+    rc |= upload(&p->d_B, B, (size_t)ob);
+    rc |= upload(&p->d_BTw, BTw, (size_t)ob);
+    rc |= upload(&p->d_D1, D1, (size_t)og);
+    rc |= upload(&p->d_D2, D2, (size_t)og);
+    if (rc) { evr_sg4_plan_destroy(&p); return 1; }
+    if (cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        evr_sg4_plan_destroy(&p); return fail("evr_sg4_plan_create: cudaStreamCreate failed");
+    }
+
+    p->smem_bytes = (size_t)2 * p->cap * sizeof(double) + (size_t)(4 * nT + 5 * D) * sizeof(int);
+    if (p->smem_bytes > 227 * 1024) { evr_sg4_plan_destroy(&p); return fail("evr_sg4_plan_create: shared-memory budget exceeded"); }
+    if (cudaFuncSetAttribute(evr::sg4_term_kernel_generic, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_bytes) != cudaSuccess) {
+        evr_sg4_plan_destroy(&p); return fail("evr_sg4_plan_create: cudaFuncSetAttribute(smem) failed");
+    }
+    int occ = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, evr::sg4_term_kernel_generic, 256, p->smem_bytes) != cudaSuccess || occ < 1) {
+        evr_sg4_plan_destroy(&p); return fail("evr_sg4_plan_create: kernel cannot be resident (occupancy 0)");
+    }
+    p->grid_ctas = std::max(1, std::min(p->n_terms, p->sm_count * occ));
+
+    evr::PlanDev &pd = p->pd;
+    pd.D = D; pd.LG = LG; pd.nb0 = nb0; pd.n_terms = p->n_terms; pd.nb = nb; pd.NQ_local = p->NQ_local;
+    pd.cap = p->cap; pd.terms = p->d_terms; pd.lev = p->d_lev; pd.map = p->d_map;
+    pd.nq_of = p->d_nq_of; pd.nb_of = p->d_nb_of; pd.offB = p->d_offB; pd.offG = p->d_offG;
+    pd.B = p->d_B; pd.BTw = p->d_BTw; pd.D1 = p->d_D1; pd.D2 = p->d_D2;
+    *out = p;
+    return 0;
+}
+
+extern "C" int evr_sg4_plan_set_op(evr_sg4_plan *p, int type_Op, int nb_Term, const int32_t *term_mode,
+                                   const uint8_t *grid_zero, const uint8_t *grid_cte,
+                                   const double *Mat_cte, const double *const *grids)
+{
+    if (!p) return fail("evr_sg4_plan_set_op: null plan");
+    if (type_Op != 0 && type_Op != 1)
+        return fail("evr_sg4_plan_set_op: type_Op must be 0 or 1 (type_Op=10 is not built yet)");
+    if (nb_Term < 1 || !grid_zero || !grid_cte) return fail("evr_sg4_plan_set_op: bad term list");
+    if (type_Op == 1 && !term_mode) return fail("evr_sg4_plan_set_op: term_mode required for type_Op=1");
+    CUDA_TRY(cudaSetDevice(p->device));
+    const int nb0 = p->nb0;
+    const int nterm = (type_Op == 0) ? 1 : nb_Term;
+    std::vector<evr::OpTermDev> ops;
+    std::vector<int> var_terms;
+    int64_t deriv_flops = 0;
+    for (int it = 0; it < nterm; ++it) {
+        if (grid_zero[it]) continue;                              // sub_OpPsi_SG4.f90:1511
+        evr::OpTermDev O{};
+        int m1 = (type_Op == 0) ? 0 : term_mode[2 * it], m2 = (type_Op == 0) ? 0 : term_mode[2 * it + 1];
+        if (m1 < 0) m1 = 0;                                         // WHERE (tab_der < 0) tab_der = 0
+        if (m2 < 0) m2 = 0;
+        if (m1 > p->D || m2 > p->D) return fail("evr_sg4_plan_set_op: term_mode out of range");
+        O.m1 = m1 - 1; O.m2 = m2 - 1;
+        if (O.m1 >= 0 && O.m2 >= 0 && O.m1 > O.m2) std::swap(O.m1, O.m2);
+        if (grid_cte[it]) {
+            if (!Mat_cte) return fail("evr_sg4_plan_set_op: Mat_cte required for grid_cte terms");
+            O.grid_slot = -1;
+            for (int i = 0; i < nb0; ++i)
+                for (int j = 0; j < nb0; ++j) O.cte[i + nb0 * j] = Mat_cte[(size_t)it * nb0 * nb0 + i + nb0 * j];
+        } else {
+            if (!grids || !grids[it]) return fail("evr_sg4_plan_set_op: missing grid for a non-constant term");
+            O.grid_slot = (int)var_terms.size();
+            var_terms.push_back(it);
+        }
+        ops.push_back(O);
+    }
+    // upload the variable grids of this plan's term range: [slot][i + nb0*j][NQ_local]
+    if (p->d_grids) { cudaFree(p->d_grids); p->d_grids = nullptr; }
+    if (p->d_opterms) { cudaFree(p->d_opterms); p->d_opterms = nullptr; }
+    const size_t blk = (size_t)std::max<int64_t>(p->NQ_local, 1);
+    const size_t ng = var_terms.size() * nb0 * nb0;
+    CUDA_TRY(cudaMalloc((void **)&p->d_grids, std::max<size_t>(ng * blk, 1) * sizeof(double)));
+    for (size_t s = 0; s < var_terms.size(); ++s)
+        for (int ij = 0; ij < nb0 * nb0; ++ij) {
+            const double *src = grids[var_terms[s]] + (size_t)ij * p->NQ_total + p->grid_start;
+            CUDA_TRY(cudaMemcpy(p->d_grids + (s * nb0 * nb0 + ij) * blk, src, (size_t)p->NQ_local * sizeof(double), cudaMemcpyHostToDevice));
+        }
+    if (upload(&p->d_opterms, ops.data(), ops.size())) return 1;
+    p->type_Op = type_Op; p->n_opterms = (int)ops.size(); p->n_var = (int)var_terms.size();
+    p->pd.type_Op = type_Op; p->pd.n_opterms = p->n_opterms; p->pd.n_var = p->n_var;
+    p->pd.opterms = p->d_opterms; p->pd.grids = p->d_grids;
+    // algorithmic flops of the operator stage
+    for (int t = 0; t < p->n_terms; ++t) {
+        const int iG = p->iG_begin + t;
+        const int64_t nq = p->h_tab_nq[iG];
+        auto nqm = [&](int m) { return (int64_t)p->h_nq_of[m * (p->LG + 1) + p->h_tab_l[(size_t)iG * p->D + m]]; };
+        for (const auto &O : ops) {
+            if (O.m1 >= 0 && O.m2 >= 0 && O.m1 != O.m2) deriv_flops += 2 * nq * (nqm(O.m1) + nqm(O.m2));
+            else if (O.m1 >= 0 || O.m2 >= 0) deriv_flops += 2 * nq * nqm(O.m1 >= 0 ? O.m1 : O.m2);
+            deriv_flops += 2 * nq * nb0;                           // pointwise multiply-add
+        }
+    }
+    p->flops_npsi1 += deriv_flops * nb0;
+    p->op_set = true;
+    return 0;
+}
+
+static int launch(evr_sg4_plan *p, int npsi, const double *d_psi, double *d_Hpsi, cudaStream_t st)
+{
+    const size_t bytes = (size_t)npsi * p->nb * p->nb0 * sizeof(double);
+    CUDA_TRY(cudaMemsetAsync(d_Hpsi, 0, bytes, st));                 // reference zeroes OpPsi (:765)
+    if (p->n_terms > 0) {
+        evr::sg4_term_kernel_generic<<<p->grid_ctas, 256, p->smem_bytes, st>>>(p->pd, npsi, d_psi, d_Hpsi);
+        CUDA_TRY(cudaGetLastError());
+        p->launches += 1;
+    }
+    return 0;
+}
+
+extern "C" int evr_sg4_apply_device(evr_sg4_plan *p, int npsi, const double *d_psi, double *d_Hpsi, void *cuda_stream)
+{
+    if (!p) return fail("evr_sg4_apply_device: null plan");
+    if (!p->op_set) return fail("evr_sg4_apply_device: operator not set (call evr_sg4_plan_set_op)");
+    if (npsi < 1) return fail("evr_sg4_apply: size(Psi) = 0");     // reference: STOP (:738-743)
+    if (!d_psi || !d_Hpsi) return fail("evr_sg4_apply_device: null buffer");
+    CUDA_TRY(cudaSetDevice(p->device));
+    return launch(p, npsi, d_psi, d_Hpsi, (cudaStream_t)cuda_stream);
+}
+
+extern "C" int evr_sg4_apply(evr_sg4_plan *p, int npsi, const double *psi, double *Hpsi)
+{
+    if (!p) return fail("evr_sg4_apply: null plan");
+    if (!p->op_set) return fail("evr_sg4_apply: operator not set (call evr_sg4_plan_set_op)");
+    if (npsi < 1) return fail("evr_sg4_apply: size(Psi) = 0");
+    if (!psi || !Hpsi) return fail("evr_sg4_apply: null buffer");
+    CUDA_TRY(cudaSetDevice(p->device));
+    const int64_t n = (int64_t)npsi * p->nb * p->nb0;
+    if (n > p->stage_cap) {
+        if (p->d_psi) cudaFree(p->d_psi);
+        if (p->d_Hpsi) cudaFree(p->d_Hpsi);
+        p->d_psi = p->d_Hpsi = nullptr; p->stage_cap = 0;
+        CUDA_TRY(cudaMalloc((void **)&p->d_psi, (size_t)n * sizeof(double)));
+        CUDA_TRY(cudaMalloc((void **)&p->d_Hpsi, (size_t)n * sizeof(double)));
+        p->stage_cap = n;
+    }
+    CUDA_TRY(cudaMemcpyAsync(p->d_psi, psi, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+    if (launch(p, npsi, p->d_psi, p->d_Hpsi, p->stream)) return 1;
+    CUDA_TRY(cudaMemcpyAsync(Hpsi, p->d_Hpsi, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+    CUDA_TRY(cudaStreamSynchronize(p->stream));
+    return 0;
+}
+
+extern "C" int64_t evr_sg4_plan_info(const evr_sg4_plan *p, int what)
+{
+    if (!p) return -1;
+    const int64_t nb0 = p->nb0;
+    switch (what) {
+    case EVR_INFO_LAUNCHES: return p->launches;
+    case EVR_INFO_ALG_BYTES_NPSI1:
+        return p->S_local * nb0 * 8 * 2 + p->S_local * 4 * 2 + p->NQ_local * nb0 * nb0 * 8 * p->n_var + p->nb * nb0 * 8 * 2;
+    case EVR_INFO_ALG_BYTES_PER_RHS_EXTRA:
+        return p->S_local * nb0 * 8 * 2 + p->nb * nb0 * 8 * 2;
+    case EVR_INFO_NQ_LOCAL: return p->NQ_local;
+    case EVR_INFO_S_LOCAL: return p->S_local;
+    case EVR_INFO_SMEM_BYTES: return (int64_t)p->smem_bytes;
+    case EVR_INFO_GRID_CTAS: return p->grid_ctas;
+    case EVR_INFO_PATH: return 0;
+    case EVR_INFO_FLOPS_NPSI1: return p->flops_npsi1;
+    default: return -1;
+    }
+}
+
+extern "C" int evr_sg4_plan_destroy(evr_sg4_plan **pp)
+{
+    if (!pp || !*pp) return 0;
+    evr_sg4_plan *p = *pp;
+    cudaSetDevice(p->device);
+    cudaFree(p->d_terms); cudaFree(p->d_lev); cudaFree(p->d_map); cudaFree(p->d_nq_of); cudaFree(p->d_nb_of);
+    cudaFree(p->d_offB); cudaFree(p->d_offG); cudaFree(p->d_B); cudaFree(p->d_BTw); cudaFree(p->d_D1); cudaFree(p->d_D2);
+    cudaFree(p->d_opterms); cudaFree(p->d_grids); cudaFree(p->d_psi); cudaFree(p->d_Hpsi);
+    if (p->stream) cudaStreamDestroy(p->stream);
+    delete p;
+    *pp = nullptr;
+    return 0;
+}

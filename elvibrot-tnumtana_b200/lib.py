@@ -1,0 +1,90 @@
+"""ctypes binding of libevr_sg4.so (the C-ABI declared in include/evr_sg4.h).
+
+The library is built in-tree by ``build()`` (nvcc, sm_100a only) and loaded from the package
+directory.  There is no fallback of any kind: if the shared object is missing or a CUDA call
+fails, an exception is raised.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+SO_PATH = os.path.join(_HERE, "libevr_sg4.so")
+_lib = None
+
+# enum values of include/evr_sg4.h
+TAB_NB_SG, TAB_NB, TAB_S, TAB_NQ, TAB_COUNT0, TAB_LMIN = 0, 1, 2, 3, 4, 5
+TAB_TAB_L, TAB_WEIGHT, TAB_TAB_NQ, TAB_TAB_NB, TAB_SUM_NQ, TAB_SUM_NB, TAB_PACKEDB, TAB_MAP = 10, 11, 12, 13, 14, 15, 16, 17
+INFO_LAUNCHES, INFO_ALG_BYTES_NPSI1, INFO_ALG_BYTES_PER_RHS_EXTRA, INFO_NQ_LOCAL, INFO_S_LOCAL = 0, 1, 2, 3, 4
+INFO_SMEM_BYTES, INFO_GRID_CTAS, INFO_PATH, INFO_FLOPS_NPSI1 = 5, 6, 7, 8
+
+EXPORTS = [
+    "evr_sg4_version", "evr_sg4_last_error",
+    "evr_sg4_tables_build", "evr_sg4_tables_destroy", "evr_sg4_tables_size", "evr_sg4_tables_get",
+    "evr_sg4_ini_iGs",
+    "evr_sg4_plan_create", "evr_sg4_plan_set_op", "evr_sg4_apply", "evr_sg4_apply_device",
+    "evr_sg4_plan_info", "evr_sg4_plan_destroy",
+]
+
+
+class EvrSg4Error(RuntimeError):
+    pass
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile csrc/ into libevr_sg4.so with nvcc for sm_100a (cross-compiles without a GPU)."""
+    srcdir = os.path.join(_HERE, "csrc")
+    srcs = [os.path.join(srcdir, f) for f in os.listdir(srcdir)] + [os.path.join(_HERE, "..", "include", "evr_sg4.h")]
+    stale = (not os.path.exists(SO_PATH)) or any(os.path.getmtime(s) > os.path.getmtime(SO_PATH) for s in srcs)
+    if force or stale:
+        cmd = ["make", "-C", srcdir] + (["-B"] if force else [])
+        out = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        if verbose or out.returncode != 0:
+            print(out.stdout)
+        if out.returncode != 0:
+            raise EvrSg4Error("nvcc build of libevr_sg4.so failed")
+    return SO_PATH
+
+
+def lib():
+    """Load the shared object (building it first if the sources are newer)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(SO_PATH):
+        build()
+    L = C.CDLL(SO_PATH)
+    vp, i32, i64 = C.c_void_p, C.c_int, C.c_int64
+    L.evr_sg4_version.restype = i32
+    L.evr_sg4_last_error.restype = C.c_char_p
+    L.evr_sg4_tables_build.restype = i32
+    L.evr_sg4_tables_build.argtypes = [C.POINTER(vp), i32, i32, i32, vp, vp]
+    L.evr_sg4_tables_destroy.argtypes = [C.POINTER(vp)]
+    L.evr_sg4_tables_size.restype = i64
+    L.evr_sg4_tables_size.argtypes = [vp, i32]
+    L.evr_sg4_tables_get.restype = i32
+    L.evr_sg4_tables_get.argtypes = [vp, i32, vp]
+    L.evr_sg4_ini_iGs.restype = i32
+    L.evr_sg4_ini_iGs.argtypes = [i32, i32, i32, C.POINTER(i32), C.POINTER(i32)]
+    L.evr_sg4_plan_create.restype = i32
+    L.evr_sg4_plan_create.argtypes = [C.POINTER(vp), i32, i32, i32, i32, i64, i32] + [vp] * 11 + [i32, i32]
+    L.evr_sg4_plan_set_op.restype = i32
+    L.evr_sg4_plan_set_op.argtypes = [vp, i32, i32, vp, vp, vp, vp, vp]
+    L.evr_sg4_apply.restype = i32
+    L.evr_sg4_apply.argtypes = [vp, i32, vp, vp]
+    L.evr_sg4_apply_device.restype = i32
+    L.evr_sg4_apply_device.argtypes = [vp, i32, vp, vp, vp]
+    L.evr_sg4_plan_info.restype = i64
+    L.evr_sg4_plan_info.argtypes = [vp, i32]
+    L.evr_sg4_plan_destroy.restype = i32
+    L.evr_sg4_plan_destroy.argtypes = [C.POINTER(vp)]
+    _lib = L
+    return L
+
+
+def check(rc: int, what: str = ""):
+    if rc != 0:
+        msg = lib().evr_sg4_last_error().decode(errors="replace")
+        raise EvrSg4Error(f"{what}: {msg}" if what else msg)

@@ -1,0 +1,138 @@
+/*
+ * evr_sg4.h -- C-ABI of the B200-native H|psi> (OpPsi) action on the Smolyak
+ * type-4 sparse grid of ElVibRot-TnumTana.
+ *
+ * This is the drop-in boundary: the body of the reference's
+ *     SUBROUTINE sub_TabOpPsi_FOR_SGtype4(Psi,OpPsi,para_Op)
+ *         Source_ElVibRot/sub_Operator/sub_OpPsi_SG4.f90:678-979
+ * (and, in MPI builds, Action_MPI_S1, sub_OpPsi_SG4_MPI.f90:454-571) is replaced
+ * by  plan_create (first call) + apply (every call).  The ISO_C_BINDING shim a
+ * maintainer adds on the Fortran side is shown in INTEGRATION.md and shipped as
+ * elvibrot-tnumtana_b200/fortran/evr_sg4_shim.f90.
+ *
+ * Conventions (same as the reference's own C bindings, TnumTana_Lib.f90:655-740):
+ * flat contiguous arrays with explicit sizes, column-major matrices, table
+ * ENTRIES keep their Fortran 1-based values (a mapping entry 0 means "dropped").
+ * Every function returns 0 on success, non-zero on error; evr_sg4_last_error()
+ * gives the message (the reference STOPs with a message; the shim does the same).
+ * Not re-entrant per plan: one caller at a time, like para_Op (intent(inout)).
+ * There is NO CPU fallback: if no CUDA device is usable the calls fail.
+ */
+#ifndef EVR_SG4_H
+#define EVR_SG4_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct evr_sg4_plan   evr_sg4_plan;
+typedef struct evr_sg4_tables evr_sg4_tables;
+
+int         evr_sg4_version(void);
+const char *evr_sg4_last_error(void);
+
+/* ---------------------------------------------------------------------------
+ * SG4 index / term tables (host, integer, bit-exact with the reference).
+ * Replaces the table part of RecSparseGrid_ForDP_type4
+ *   (Source_ElVibRot/sub_Basis/sub_quadra_SparseBasis.f90:1130-1362):
+ *   nDindB (type 5, Source_Lib/sub_nDindex/sub_module_nDindex.f90:971-1082),
+ *   nDind_SmolyakRep (type -5, :1083-1185), WeightSG
+ *   (sub_module_param_SGType2.f90:784-806), tab_nq/nb_OF_SRep (+sums,
+ *   sub_quadra_SparseBasis.f90:1315-1345) and tab_iB_OF_SRep_TO_iB
+ *   (Set_tables_FOR_SmolyakRepBasis_TO_tabPackedBasis,
+ *   sub_Basis_SG4/sub_module_basis_BtoG_GtoB_SG4.f90:625-949).
+ * Inputs: nq_of/nb_of[k*(LG+1)+L] = nq_k(L), nb_k(L) of tab_basisPrimSG(L,k).
+ * ------------------------------------------------------------------------- */
+int evr_sg4_tables_build(evr_sg4_tables **out, int D, int LB, int LG,
+                         const int32_t *nq_of, const int32_t *nb_of);
+int evr_sg4_tables_destroy(evr_sg4_tables **t);
+
+enum {                           /* 'what' for evr_sg4_tables_size / _get             */
+    EVR_TAB_NB_SG   = 0,         /* scalar: number of Smolyak terms                   */
+    EVR_TAB_NB      = 1,         /* scalar: packed basis size (nDindB%Max_nDI)        */
+    EVR_TAB_S       = 2,         /* scalar: sum_iG nb(iG)  (Max_Srep)                 */
+    EVR_TAB_NQ      = 3,         /* scalar: sum_iG nq(iG)                             */
+    EVR_TAB_COUNT0  = 4,         /* scalar: number of zero entries of the map         */
+    EVR_TAB_LMIN    = 5,         /* scalar: Lmin = max(0, LG-D+1)                     */
+    EVR_TAB_TAB_L   = 10,        /* int32 [nb_SG][D]   Tab_nDval(:,iG) of the terms   */
+    EVR_TAB_WEIGHT  = 11,        /* double[nb_SG]      WeightSG                       */
+    EVR_TAB_TAB_NQ  = 12,        /* int32 [nb_SG]      tab_nq_OF_SRep                 */
+    EVR_TAB_TAB_NB  = 13,        /* int32 [nb_SG]      tab_nb_OF_SRep                 */
+    EVR_TAB_SUM_NQ  = 14,        /* int64 [nb_SG]      tab_Sum_nq_OF_SRep (inclusive) */
+    EVR_TAB_SUM_NB  = 15,        /* int64 [nb_SG]      tab_Sum_nb_OF_SRep (inclusive) */
+    EVR_TAB_PACKEDB = 16,        /* int32 [nb][D]      nDindB%Tab_nDval(:,iB)         */
+    EVR_TAB_MAP     = 17         /* int32 [S]          tab_iB_OF_SRep_TO_iB           */
+};
+int64_t evr_sg4_tables_size(const evr_sg4_tables *t, int what);   /* scalar value or element count */
+int     evr_sg4_tables_get(const evr_sg4_tables *t, int what, void *dst); /* copy an array out */
+
+/* Term range of one rank: ini_iGs_MPI,
+ * sub_Basis_SG4/sub_module_basis_BtoG_GtoB_SG4_MPI.f90:639-669 (0-based, end exclusive). */
+int evr_sg4_ini_iGs(int nb_SG, int np, int rank, int *iG_begin, int *iG_end);
+
+/* ---------------------------------------------------------------------------
+ * Plan = device-resident copy of everything sub_TabOpPsi_FOR_SGtype4 reads from
+ * para_Op%BasisnD (param_SGType2, WeightSG, tab_basisPrimSG), for the terms
+ * [iG_begin, iG_end) of this process (all terms: 0, nb_SG).
+ *   tab_l[iG*D+k]           nDind_SmolyakRep%Tab_nDval(k,iG)
+ *   tab_iB[S]               tab_iB_OF_SRep_TO_iB (full table; the slice is taken here)
+ *   nq_of/nb_of[k*(LG+1)+L]
+ *   B, BTw, D1, D2          concatenation over k = 0..D-1 (outer), L = 0..LG (inner) of
+ *                           dnRGB%d0(nq,nb), dnRBGwrho%d0(nb,nq), dnRGG%d1(nq,nq,1),
+ *                           dnRGG%d2(nq,nq,1,1), each column-major.
+ * device < 0 : use the current CUDA device.
+ * ------------------------------------------------------------------------- */
+int evr_sg4_plan_create(evr_sg4_plan **plan, int device,
+                        int D, int nb_SG, int nb0, int64_t nb, int LG,
+                        const int32_t *tab_l, const double *WeightSG,
+                        const int32_t *tab_nq_OF_SRep, const int32_t *tab_nb_OF_SRep,
+                        const int32_t *tab_iB,
+                        const int32_t *nq_of, const int32_t *nb_of,
+                        const double *B, const double *BTw, const double *D1, const double *D2,
+                        int iG_begin, int iG_end);
+
+/* Operator description = para_Op%{type_Op, nb_Term, derive_termQdyn, OpGrid(:)}
+ * (sub_OpPsi_SG4.f90:1447-1546; term numbering Init_TypeOp,
+ * Source_PrimOperator/sub_module_SimpleOp.f90:256-375).
+ *   type_Op   0 (scalar operator, one term) or 1 (H = sum_iterm F_iterm(Q) d^(i,j)).
+ *   term_mode[2*iterm+{0,1}]  1-based SG4 mode owning each index of
+ *             derive_termQdyn(:,iterm) through Tabder_Qdyn_TO_Qbasis; 0 = none.
+ *   grid_zero/grid_cte[iterm] OpGrid(iterm)%grid_zero / %grid_cte.
+ *   Mat_cte[iterm*nb0*nb0 + j + nb0*i] = OpGrid(iterm)%Mat_cte(j,i).
+ *   grids[iterm]  NULL for zero/cte terms, else OpGrid(iterm)%Grid(1:NQ,1:nb0,1:nb0)
+ *             (column-major, the whole Smolyak grid; term offset tab_Sum_nq-nq).
+ * The grids are copied to the device once (they are immutable after the first
+ * H|psi>, Save_MemGrid_done). */
+int evr_sg4_plan_set_op(evr_sg4_plan *plan, int type_Op, int nb_Term,
+                        const int32_t *term_mode,
+                        const uint8_t *grid_zero, const uint8_t *grid_cte,
+                        const double *Mat_cte, const double *const *grids);
+
+/* H|psi> for npsi real right-hand sides (complex psi = 2 real RHS, sub_OpPsi.f90:392-407).
+ * psi/Hpsi[ipsi*nb*nb0 + ib0*nb + iB]  (= Psi(ipsi)%RvecB).  Hpsi is overwritten
+ * (the reference zeroes it, sub_OpPsi_SG4.f90:765); with a term sub-range it holds
+ * this rank's partial sum (to be summed over ranks: MPI_Reduce_sum_Bcast / NCCL). */
+int evr_sg4_apply(evr_sg4_plan *plan, int npsi, const double *psi, double *Hpsi);          /* host buffers   */
+int evr_sg4_apply_device(evr_sg4_plan *plan, int npsi, const double *d_psi, double *d_Hpsi,
+                         void *cuda_stream);                                               /* device buffers */
+
+enum {                           /* 'what' for evr_sg4_plan_info */
+    EVR_INFO_LAUNCHES        = 0,   /* kernels launched by this plan so far            */
+    EVR_INFO_ALG_BYTES_NPSI1 = 1,   /* algorithmic bytes of one H|psi>, npsi = 1       */
+    EVR_INFO_ALG_BYTES_PER_RHS_EXTRA = 2, /* additional bytes per extra RHS            */
+    EVR_INFO_NQ_LOCAL        = 3,   /* grid points in this plan's term range           */
+    EVR_INFO_S_LOCAL         = 4,   /* term-local basis coefficients in the range      */
+    EVR_INFO_SMEM_BYTES      = 5,   /* dynamic shared memory per CTA                   */
+    EVR_INFO_GRID_CTAS       = 6,   /* CTAs per launch                                 */
+    EVR_INFO_PATH            = 7,   /* 0 = generic term kernel, 1 = constant-KEO fast path */
+    EVR_INFO_FLOPS_NPSI1     = 8    /* algorithmic flops of one H|psi>      */
+};
+int64_t evr_sg4_plan_info(const evr_sg4_plan *plan, int what);
+int     evr_sg4_plan_destroy(evr_sg4_plan **plan);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EVR_SG4_H */

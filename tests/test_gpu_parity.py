@@ -1,0 +1,143 @@
+"""Parity of the CUDA path (through the C-ABI) against the CPU oracle.  Tolerance: relative L2
+<= 1e-12 per right-hand side (north star), eigenvalues <= 1e-6 cm^-1 = 4.6e-12 au against the oracle."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from helpers import oracle_apply, random_psi, rel_l2
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-12
+CM1_IN_AU = 1.0 / 219474.631363
+
+
+def _check(op, npsi, seed=12345, tol=TOL):
+    b = op.BasisnD
+    psi = random_psi(b.nb * b.nb0, npsi, seed)
+    ref = oracle_apply(op, psi)
+    out = op.apply_host(psi)
+    for i in range(npsi):
+        assert rel_l2(out[i], ref[i]) < tol, (i, rel_l2(out[i], ref[i]))
+    return out, ref
+
+
+@pytest.mark.parametrize("D,L,npsi", [(6, 3, 1), (6, 3, 5), (12, 2, 2), (12, 3, 1), (12, 4, 3), (21, 2, 2), (3, 5, 1), (1, 4, 2), (2, 0, 1)])
+def test_henon_heiles_parity(evr, D, L, npsi):
+    basis, op = evr.workloads.henon_heiles(D, L)
+    _check(op, npsi)
+    assert op.info(evr.lib.INFO_LAUNCHES) >= 1
+
+
+def test_lb_smaller_than_lg_dropped_functions(evr):
+    """LB < LG: mapping entries 0 -> read as 0 on gather, skipped on scatter."""
+    basis, op = evr.workloads.henon_heiles(5, 4, LB=2)
+    assert basis.count0 > 0
+    _check(op, 2)
+
+
+def test_pyrazine_two_states_complex_psi(evr):
+    """nb0 = 2, 2x2 potential matrix on the grid, complex psi handled as two real right-hand sides."""
+    basis, op = evr.workloads.pyrazine_12d(1)
+    assert (basis.nb_SG, basis.nb, basis.nqq) == (13, 27, 39)
+    n = basis.nb * 2
+    rng = np.random.default_rng(3)
+    c = rng.standard_normal(n) + 1j * rng.standard_normal(n)
+    psi, Hpsi = evr.ParamPsi.complex(c), evr.ParamPsi()
+    evr.sub_OpPsi(psi, Hpsi, op)
+    ref = oracle_apply(op, np.stack([c.real, c.imag]))
+    assert Hpsi.cplx
+    assert rel_l2(Hpsi.CvecB.real, ref[0]) < TOL and rel_l2(Hpsi.CvecB.imag, ref[1]) < TOL
+    basis2, op2 = evr.workloads.pyrazine_12d(2)
+    _check(op2, 2)
+
+
+def test_hcn_shape_curvilinear(evr):
+    """HCN_UT shape: 3 modes (10+10L, 1+2L, 1+2L), LB=4/LG=5 guess run and LB=6/LG=7, all 10 term
+    grids variable, mixed derivatives d1 x d1 (synthetic N(0,1) operator grids)."""
+    for LB, LG, sizes in [(4, 5, (46, 850, 9230)), (6, 7, (85, 2310, 36200))]:
+        basis = evr.workloads.hm_sg4_basis(3, LB, LG, [10, 1, 1], [10, 2, 2])
+        assert (basis.nb_SG, basis.nb, basis.nqq) == sizes
+        op = evr.workloads.synthetic_curvilinear(basis)
+        assert op.nb_Term == 10
+        _check(op, 2)
+
+
+def test_hno3_shape_curvilinear(evr):
+    """HNO3_UT inner SG4 shape: 8 modes nq=nb=1+L, LB=2/LG=4, nb_Term = 45 (all grids variable)."""
+    basis = evr.workloads.hm_sg4_basis(8, 2, 4, 1, 1)
+    assert (basis.nb_SG, basis.nb, basis.nqq, basis.count0) == (495, 45, 4845, 1410)
+    op = evr.workloads.synthetic_curvilinear(basis)
+    assert op.nb_Term == 45
+    _check(op, 1)
+
+
+def test_type_op_0_scalar_operator(evr):
+    basis = evr.workloads.hm_sg4_basis(4, 3, 3, 1, 2, nb0=2)
+    rng = np.random.default_rng(5)
+    g = np.asfortranarray(rng.standard_normal((basis.nqq, 2, 2)))
+    op = evr.ParamOp(basis, 0, [evr.OpGrid((0, 0), Grid=g)])
+    _check(op, 2)
+
+
+def test_term_ranges_sum_to_full_action(evr):
+    """MPI scheme 1 decomposition: plans over ini_iGs ranges give partial sums that add up."""
+    basis, op = evr.workloads.henon_heiles(6, 3)
+    psi = random_psi(basis.nb, 2, 7)
+    full = op.apply_host(psi)
+    L = evr.lib.lib()
+    acc = np.zeros_like(full)
+    for r in range(3):
+        b, e = C.c_int(), C.c_int()
+        assert L.evr_sg4_ini_iGs(basis.nb_SG, 3, r, C.byref(b), C.byref(e)) == 0
+        part = evr.ParamOp(basis, 1, op.OpGrid, iG_range=(b.value, e.value))
+        acc += part.apply_host(psi)
+    assert rel_l2(acc, full) < TOL
+    assert rel_l2(full, oracle_apply(op, psi)) < TOL
+
+
+def test_gpu_eigenvalues_match_reference_and_oracle(evr, golden):
+    """H matrix built column by column with the CUDA path (block of nb unit vectors, as
+    Sub_OpPsi_test does, vib.f90:1507): eigenvalues vs oracle <= 1e-6 cm^-1, vs reference benchmark 2e-7 au."""
+    basis, op = evr.workloads.henon_heiles(6, 3)
+    I = np.eye(basis.nb)
+    Hg = op.apply_host(I).T
+    Ho = oracle_apply(op, I).T
+    eg = np.sort(np.linalg.eigvals(Hg).real)
+    eo = np.sort(np.linalg.eigvals(Ho).real)
+    assert np.abs(eg - eo).max() < 1e-6 * CM1_IN_AU
+    ref = np.array(golden["kat"]["HH6D_L3"]["levels"])
+    assert np.abs(eg[: len(ref)] - ref).max() < 2e-7
+
+
+def test_error_behaviour_mirrors_reference(evr):
+    basis, op = evr.workloads.henon_heiles(3, 2)
+    with pytest.raises(evr.EvrStop):                      # STOP: size(Psi) = 0  (sub_OpPsi_SG4.f90:738-743)
+        evr.sub_TabOpPsi_FOR_SGtype4([], [], op)
+    with pytest.raises(evr.EvrStop):                      # STOP: Psi(1) is complex (:744-749)
+        evr.sub_TabOpPsi_FOR_SGtype4([evr.ParamPsi.complex(np.zeros(basis.nb))], [], op)
+    L = evr.lib.lib()
+    z = np.zeros(basis.nb)
+    assert L.evr_sg4_apply(op.plan(), 0, z.ctypes.data, z.ctypes.data) != 0
+    assert b"size(Psi)" in L.evr_sg4_last_error()
+
+
+def test_linearity_and_repeatability(evr):
+    basis, op = evr.workloads.henon_heiles(12, 4)
+    psi = random_psi(basis.nb, 2, 11)
+    a = op.apply_host(psi)
+    lin = op.apply_host((2.0 * psi[0] - 3.0 * psi[1])[None, :])[0]
+    assert rel_l2(lin, 2.0 * a[0] - 3.0 * a[1]) < 1e-12
+    b = op.apply_host(psi)
+    assert rel_l2(a, b) < 1e-13       # atomics reorder the sum: reproducible to rounding only (like the reference's OMP ATOMIC)
+
+
+def test_device_entry_point_with_torch(evr):
+    import torch
+    basis, op = evr.workloads.henon_heiles(12, 3)
+    psi = random_psi(basis.nb, 3, 13)
+    d_psi = torch.from_numpy(psi).cuda()
+    d_out = torch.full_like(d_psi, 7.0)                   # must be overwritten, not accumulated
+    op.apply_device_ptr(3, d_psi.data_ptr(), d_out.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert rel_l2(d_out.cpu().numpy(), oracle_apply(op, psi)) < TOL
