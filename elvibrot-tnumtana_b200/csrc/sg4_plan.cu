@@ -7,12 +7,14 @@
 #include "../../include/evr_sg4.h"
 #include "sg4_internal.h"
 #include "sg4_kernels.cuh"
+#include "sg4_fast.cuh"
 
 #include <cuda_runtime.h>
 
 #include <algorithm>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <numeric>
 #include <string>
 #include <vector>
@@ -49,6 +51,18 @@ struct evr_sg4_plan {
     // host copies needed later
     std::vector<int32_t> h_tab_l, h_nq_of, h_nb_of, h_tab_nq, h_tab_nb;
     std::vector<int> order;                 // work order -> local term index
+    std::vector<int32_t> h_map;             // mapping slice of the range (reference order)
+    std::vector<int64_t> h_map_off, h_grid_off;   // per local term (reference order)
+    std::vector<double> h_B, h_BTw, h_D1, h_D2, h_weight;
+    std::vector<int32_t> h_offB, h_offG;
+    // fast path (sg4_fast.cuh)
+    bool fast = false;
+    evr::FastTermDev *d_fterms = nullptr;
+    int32_t *d_fmap = nullptr;
+    double *d_fmats = nullptr, *d_fV = nullptr;
+    evr::FastPlanDev fpd{};
+    size_t fast_smem = 0;
+    int fast_ctas = 0;
     // device
     evr::TermDev *d_terms = nullptr;
     uint8_t *d_lev = nullptr;
@@ -168,6 +182,16 @@ extern "C" int evr_sg4_plan_create(evr_sg4_plan **out, int device,
                     std::to_string(cap * nb0) + " doubles)");
     }
     p->cap = (int)(cap * nb0);
+    p->h_map.assign(tab_iB + map_start, tab_iB + map_start + p->S_local);
+    p->h_map_off.resize(p->n_terms); p->h_grid_off.resize(p->n_terms);
+    for (int t = 0; t < p->n_terms; ++t) {
+        p->h_map_off[t] = pre_nb[iG_begin + t] - map_start;
+        p->h_grid_off[t] = pre_nq[iG_begin + t] - p->grid_start;
+    }
+    p->h_B.assign(B, B + ob); p->h_BTw.assign(BTw, BTw + ob);
+    p->h_D1.assign(D1, D1 + og); p->h_D2.assign(D2, D2 + og);
+    p->h_weight.assign(WeightSG, WeightSG + nb_SG);
+    p->h_offB = offB; p->h_offG = offG;
     p->order.resize(p->n_terms);
     std::iota(p->order.begin(), p->order.end(), 0);
     std::stable_sort(p->order.begin(), p->order.end(), [&](int a, int b) { return cost[a] > cost[b]; });
@@ -218,6 +242,183 @@ extern "C" int evr_sg4_plan_create(evr_sg4_plan **out, int device,
     pd.nq_of = p->d_nq_of; pd.nb_of = p->d_nb_of; pd.offB = p->d_offB; pd.offG = p->d_offG;
     pd.B = p->d_B; pd.BTw = p->d_BTw; pd.D1 = p->d_D1; pd.D2 = p->d_D2;
     *out = p;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Fast path set-up (sg4_fast.cuh): returns 0 and sets p->fast when the operator qualifies,
+// returns 0 with p->fast == false when it does not (generic kernel is used), 1 on CUDA errors.
+// ------------------------------------------------------------------------------------------------
+static int fast_template_id(int n1, int n2)
+{
+#define X(id, a, b) if (n1 == a && ((b == 1 && n2 == 0) || (b > 1 && n2 == b))) return id;
+    EVR_TMPL_LIST(X)
+#undef X
+    return 0;
+}
+static bool fast_pair_supported(int a, int b)   // a <= b
+{
+    if (a < 2) return false;
+    return fast_template_id(a, b) != 0;
+}
+
+static int build_fast_path(evr_sg4_plan *p, int nb_Term, const int32_t *term_mode,
+                           const uint8_t *grid_zero, const uint8_t *grid_cte,
+                           const double *Mat_cte, const double *const *grids)
+{
+    p->fast = false;
+    if (getenv("EVR_SG4_FORCE_GENERIC")) return 0;
+    const int D = p->D, LG = p->LG, nb0 = p->nb0, nT = D * (LG + 1);
+    for (int i = 0; i < nT; ++i) if (p->h_nq_of[i] != p->h_nb_of[i]) return 0;
+    const int nterm = (p->type_Op == 0) ? 1 : nb_Term;
+    std::vector<double> c1(D, 0.0), c2(D, 0.0);
+    double c00 = 0.0;
+    const double *Vgrid = nullptr;
+    for (int it = 0; it < nterm; ++it) {
+        if (grid_zero[it]) continue;
+        int m1 = (p->type_Op == 0) ? 0 : std::max(0, (int)term_mode[2 * it]);
+        int m2 = (p->type_Op == 0) ? 0 : std::max(0, (int)term_mode[2 * it + 1]);
+        double c = 0.0;
+        if (grid_cte[it]) {
+            const double *M = Mat_cte + (size_t)it * nb0 * nb0;
+            c = M[0];
+            for (int i = 0; i < nb0; ++i)
+                for (int j = 0; j < nb0; ++j)
+                    if (M[i + nb0 * j] != ((i == j) ? c : 0.0)) return 0;   // must be c * identity
+        }
+        if (m1 == 0 && m2 == 0) {
+            if (grid_cte[it]) c00 += c;
+            else { if (Vgrid) return 0; Vgrid = grids[it]; }
+        } else {
+            if (!grid_cte[it]) return 0;                                     // variable KEO grid -> generic
+            if (m1 != 0 && m2 != 0 && m1 != m2) return 0;                    // mixed derivative -> generic
+            const int k = (m1 != 0 ? m1 : m2) - 1;
+            if (m1 == m2) c2[k] += c; else c1[k] += c;
+        }
+    }
+    // matrix pool [B|BTw|T] per (k,L)
+    std::vector<int> moff(nT);
+    std::vector<double> pool;
+    for (int k = 0; k < D; ++k)
+        for (int L = 0; L <= LG; ++L) {
+            const int i = k * (LG + 1) + L, n = p->h_nq_of[i];
+            moff[i] = (int)pool.size();
+            const double *Bm = p->h_B.data() + p->h_offB[i], *Wm = p->h_BTw.data() + p->h_offB[i];
+            const double *d1 = p->h_D1.data() + p->h_offG[i], *d2 = p->h_D2.data() + p->h_offG[i];
+            pool.insert(pool.end(), Bm, Bm + n * n);
+            pool.insert(pool.end(), Wm, Wm + n * n);
+            for (int e = 0; e < n * n; ++e) pool.push_back(c2[k] * d2[e] + c1[k] * d1[e]);
+        }
+    // per-term schedules + permutation to the internal layout
+    std::vector<evr::FastTermDev> fterms(p->n_terms);
+    std::vector<int32_t> fmap((size_t)std::max<int64_t>(p->S_local, 1));
+    std::vector<double> fV;
+    if (Vgrid) fV.resize((size_t)nb0 * nb0 * std::max<int64_t>(p->NQ_local, 1));
+    int matcap = 1;
+    bool ok = true;
+#pragma omp parallel for schedule(dynamic, 64) reduction(max:matcap)
+    for (int w = 0; w < p->n_terms; ++w) {
+        if (!ok) continue;
+        const int t = p->order[w], iG = p->iG_begin + t;
+        evr::FastTermDev &F = fterms[w];
+        std::memset(&F, 0, sizeof(F));
+        F.map_off = p->h_map_off[t]; F.grid_off = p->h_grid_off[t];
+        F.nq = p->h_tab_nq[iG];
+        double wgt = p->h_weight[iG], shift = c00;
+        // active modes (size > 1), sorted by size
+        struct Act { int k, n, refstride; };
+        std::vector<Act> act;
+        int refstride = 1;
+        for (int k = 0; k < D; ++k) {
+            const int l = p->h_tab_l[(size_t)iG * D + k], i = k * (LG + 1) + l, n = p->h_nq_of[i];
+            if (n == 1) {
+                const double *blk = pool.data() + moff[i];
+                wgt *= blk[0] * blk[1];
+                shift += blk[2];
+            } else act.push_back({k, n, refstride});
+            refstride *= n;
+        }
+        std::stable_sort(act.begin(), act.end(), [](const Act &a, const Act &b) { return a.n < b.n; });
+        struct Grp { int a1, a2; };            // indices into act; a2 = -1 single
+        std::vector<Grp> grp;
+        int lo = 0, hi = (int)act.size() - 1;
+        while (lo <= hi) {
+            if (lo < hi && fast_pair_supported(act[lo].n, act[hi].n)) { grp.push_back({lo, hi}); ++lo; --hi; }
+            else { grp.push_back({hi, -1}); --hi; }
+        }
+        auto gsize = [&](const Grp &g) { return act[g.a1].n * (g.a2 >= 0 ? act[g.a2].n : 1); };
+        std::stable_sort(grp.begin(), grp.end(), [&](const Grp &a, const Grp &b) { return gsize(a) > gsize(b); });
+        if ((int)grp.size() > EVR_MAXG) { ok = false; continue; }
+        F.ngroups = (int)grp.size();
+        F.weight = wgt; F.vshift = shift;
+        // internal mode order and strides
+        std::vector<int> in_n, in_ref;          // per internal mode: size, reference stride
+        int stride = 1, mats = 0;
+        for (size_t g = 0; g < grp.size(); ++g) {
+            const Act &A1 = act[grp[g].a1];
+            evr::FastGroup &Gd = F.g[g];
+            Gd.stride = stride;
+            Gd.n1 = (unsigned short)A1.n;
+            const int l1 = p->h_tab_l[(size_t)iG * D + A1.k];
+            Gd.mat1 = moff[A1.k * (LG + 1) + l1];
+            in_n.push_back(A1.n); in_ref.push_back(A1.refstride);
+            stride *= A1.n; mats += 3 * A1.n * A1.n;
+            if (grp[g].a2 >= 0) {
+                const Act &A2 = act[grp[g].a2];
+                Gd.n2 = (unsigned short)A2.n;
+                const int l2 = p->h_tab_l[(size_t)iG * D + A2.k];
+                Gd.mat2 = moff[A2.k * (LG + 1) + l2];
+                in_n.push_back(A2.n); in_ref.push_back(A2.refstride);
+                stride *= A2.n; mats += 3 * A2.n * A2.n;
+            } else { Gd.n2 = 0; Gd.mat2 = Gd.mat1; }
+            Gd.tmpl = (unsigned short)fast_template_id(Gd.n1, Gd.n2);
+            if (Gd.tmpl == 0 && (Gd.n2 != 0 || Gd.n1 > EVR_RT_NMAX)) ok = false;
+        }
+        matcap = std::max(matcap, mats);
+        // permutation: internal index q' -> reference index q (odometer over internal modes)
+        const int nm = (int)in_n.size();
+        std::vector<int> idx(nm, 0);
+        int64_t q = 0;
+        const int32_t *msrc = p->h_map.data() + F.map_off;
+        int32_t *mdst = fmap.data() + F.map_off;
+        for (int qp = 0; qp < F.nq; ++qp) {
+            mdst[qp] = msrc[q];
+            if (Vgrid)
+                for (int ij = 0; ij < nb0 * nb0; ++ij)
+                    fV[(size_t)ij * p->NQ_local + F.grid_off + qp] = Vgrid[(size_t)ij * p->NQ_total + p->grid_start + F.grid_off + q];
+            for (int m = 0; m < nm; ++m) {
+                q += in_ref[m];
+                if (++idx[m] < in_n[m]) break;
+                q -= (int64_t)in_ref[m] * in_n[m];
+                idx[m] = 0;
+            }
+        }
+    }
+    if (!ok) return 0;
+    if ((size_t)matcap * sizeof(double) > 48 * 1024) return 0;
+    int64_t cap = 1;
+    for (int t = 0; t < p->n_terms; ++t) cap = std::max<int64_t>(cap, p->h_tab_nq[p->iG_begin + t]);
+    cap *= nb0;
+    size_t smem = ((size_t)2 * cap + matcap) * sizeof(double) + sizeof(evr::FastTermDev);
+    if (smem > 200 * 1024) return 0;
+
+    cudaFree(p->d_fterms); cudaFree(p->d_fmap); cudaFree(p->d_fmats); cudaFree(p->d_fV);
+    p->d_fterms = nullptr; p->d_fmap = nullptr; p->d_fmats = nullptr; p->d_fV = nullptr;
+    if (upload(&p->d_fterms, fterms.data(), fterms.size())) return 1;
+    if (upload(&p->d_fmap, fmap.data(), fmap.size())) return 1;
+    if (upload(&p->d_fmats, pool.data(), pool.size())) return 1;
+    if (Vgrid && upload(&p->d_fV, fV.data(), fV.size())) return 1;
+    CUDA_TRY(cudaFuncSetAttribute(evr::sg4_term_kernel_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 0;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, evr::sg4_term_kernel_fast, 128, smem));
+    if (occ < 1) return 0;
+    p->fast_smem = smem;
+    p->fast_ctas = std::max(1, std::min(p->n_terms, p->sm_count * occ));
+    evr::FastPlanDev &f = p->fpd;
+    f.nb0 = nb0; f.n_terms = p->n_terms; f.cap = (int)cap; f.matcap = matcap; f.has_V = Vgrid ? 1 : 0;
+    f.nb = p->nb; f.NQ_local = p->NQ_local;
+    f.terms = p->d_fterms; f.map = p->d_fmap; f.mats = p->d_fmats; f.V = p->d_fV;
+    p->fast = true;
     return 0;
 }
 
@@ -284,6 +485,7 @@ extern "C" int evr_sg4_plan_set_op(evr_sg4_plan *p, int type_Op, int nb_Term, co
         }
     }
     p->flops_npsi1 += deriv_flops * nb0;
+    if (build_fast_path(p, nb_Term, term_mode, grid_zero, grid_cte, Mat_cte, grids)) return 1;
     p->op_set = true;
     return 0;
 }
@@ -293,7 +495,10 @@ static int launch(evr_sg4_plan *p, int npsi, const double *d_psi, double *d_Hpsi
     const size_t bytes = (size_t)npsi * p->nb * p->nb0 * sizeof(double);
     CUDA_TRY(cudaMemsetAsync(d_Hpsi, 0, bytes, st));                 // reference zeroes OpPsi (:765)
     if (p->n_terms > 0) {
-        evr::sg4_term_kernel_generic<<<p->grid_ctas, 256, p->smem_bytes, st>>>(p->pd, npsi, d_psi, d_Hpsi);
+        if (p->fast)
+            evr::sg4_term_kernel_fast<<<p->fast_ctas, 128, p->fast_smem, st>>>(p->fpd, npsi, d_psi, d_Hpsi);
+        else
+            evr::sg4_term_kernel_generic<<<p->grid_ctas, 256, p->smem_bytes, st>>>(p->pd, npsi, d_psi, d_Hpsi);
         CUDA_TRY(cudaGetLastError());
         p->launches += 1;
     }
@@ -345,9 +550,9 @@ extern "C" int64_t evr_sg4_plan_info(const evr_sg4_plan *p, int what)
         return p->S_local * nb0 * 8 * 2 + p->nb * nb0 * 8 * 2;
     case EVR_INFO_NQ_LOCAL: return p->NQ_local;
     case EVR_INFO_S_LOCAL: return p->S_local;
-    case EVR_INFO_SMEM_BYTES: return (int64_t)p->smem_bytes;
-    case EVR_INFO_GRID_CTAS: return p->grid_ctas;
-    case EVR_INFO_PATH: return 0;
+    case EVR_INFO_SMEM_BYTES: return (int64_t)(p->fast ? p->fast_smem : p->smem_bytes);
+    case EVR_INFO_GRID_CTAS: return p->fast ? p->fast_ctas : p->grid_ctas;
+    case EVR_INFO_PATH: return p->fast ? 1 : 0;
     case EVR_INFO_FLOPS_NPSI1: return p->flops_npsi1;
     default: return -1;
     }
@@ -361,6 +566,7 @@ extern "C" int evr_sg4_plan_destroy(evr_sg4_plan **pp)
     cudaFree(p->d_terms); cudaFree(p->d_lev); cudaFree(p->d_map); cudaFree(p->d_nq_of); cudaFree(p->d_nb_of);
     cudaFree(p->d_offB); cudaFree(p->d_offG); cudaFree(p->d_B); cudaFree(p->d_BTw); cudaFree(p->d_D1); cudaFree(p->d_D2);
     cudaFree(p->d_opterms); cudaFree(p->d_grids); cudaFree(p->d_psi); cudaFree(p->d_Hpsi);
+    cudaFree(p->d_fterms); cudaFree(p->d_fmap); cudaFree(p->d_fmats); cudaFree(p->d_fV);
     if (p->stream) cudaStreamDestroy(p->stream);
     delete p;
     *pp = nullptr;
