@@ -40,7 +40,17 @@ struct FastTermDev {
     double weight;          // WeightSG * prod_{1x1 modes} B(0,0) BTw(0,0)
     double vshift;          // sum_{1x1 modes} T(0,0) (+ constant (0,0) term)
     int nq, ngroups;
+    long long next_map_off, next_grid_off;   // the term this thread group processes next
+    long long next2_map_off;                 // ... and the one after it (software pipeline, sg4_term_kernel_fast)
+    int next_nq, next2_nq;
     FastGroup g[EVR_MAXG];
+};
+
+struct FastClassDev {       // one launch per size class: terms [term_begin, term_begin+n_terms)
+    int term_begin, n_terms;
+    int gsize;              // threads cooperating on one term: 32, 64 or 128 (CTA = 128 threads)
+    int cap;                // doubles per psi/acc buffer (max nq*nb0 of the class)
+    int mapcap;             // int32 per mapping buffer (max nq of the class)
 };
 
 struct FastPlanDev {
@@ -137,9 +147,10 @@ enum { PASS_XFORM = 0, PASS_LAST = 1, PASS_KEO = 2 };
 struct PassArgs {
     double *psi, *acc;          // shared-memory buffers
     const double *m1, *m2;      // shared-memory [B|BTw|T] blocks of the two modes
-    const double *V;            // global, term slice (nb0 == 1 fused) or nullptr
+    const double *V;            // shared memory copy of the term's V slice (nb0 == 1 fused) or nullptr
     double vshift;
     int nq, nb0, stride;
+    int tid, nthr;              // thread index / count inside the group working on this term
     int kind;                   // PASS_*
     int which;                  // XFORM: 0 = B on psi, 1 = BTw on acc
     int fuse_g2b;               // LAST / KEO: also apply BTw of this group before storing acc
@@ -155,7 +166,7 @@ __device__ __forceinline__ void run_pass(const PassArgs &A)
     const int total = ntiles * A.nb0;
     const double *B1 = A.m1, *W1 = A.m1 + NN1, *T1 = A.m1 + 2 * NN1;
     const double *B2 = (N2 > 1) ? A.m2 : A.m1, *W2 = B2 + NN2, *T2 = B2 + 2 * NN2;
-    for (int t = threadIdx.x; t < total; t += blockDim.x) {
+    for (int t = A.tid; t < total; t += A.nthr) {
         const int c = t / ntiles;
         const int tt = t - c * ntiles;
         const int hi = tt / A.stride;
@@ -178,7 +189,7 @@ __device__ __forceinline__ void run_pass(const PassArgs &A)
                 for (int j = 0; j < N2; ++j)
 #pragma unroll
                     for (int i = 0; i < N1; ++i)
-                        a[j][i] = (__ldg(A.V + q0 + A.stride * (i + N1 * j)) + A.vshift) * v[j][i];
+                        a[j][i] = (A.V[q0 + A.stride * (i + N1 * j)] + A.vshift) * v[j][i];
             } else {
 #pragma unroll
                 for (int j = 0; j < N2; ++j)
@@ -206,7 +217,7 @@ __device__ __noinline__ void run_pass_rt(const PassArgs &A, const int n)
     const int ntiles = A.nq / n;
     const int total = ntiles * A.nb0;
     const double *B1 = A.m1, *W1 = A.m1 + nn, *T1 = A.m1 + 2 * nn;
-    for (int t = threadIdx.x; t < total; t += blockDim.x) {
+    for (int t = A.tid; t < total; t += A.nthr) {
         const int c = t / ntiles;
         const int tt = t - c * ntiles;
         const int hi = tt / A.stride;
@@ -239,7 +250,7 @@ __device__ __noinline__ void run_pass_rt(const PassArgs &A, const int n)
                 for (int i = 0; i < EVR_RT_NMAX; ++i) if (i < n) {
                     v[i] = r[i];
                     if (A.store_psi) A.psi[base + A.stride * i] = r[i];
-                    a[i] = ((A.V ? __ldg(A.V + q0 + A.stride * i) : 0.0) + A.vshift) * r[i];
+                    a[i] = ((A.V ? A.V[q0 + A.stride * i] : 0.0) + A.vshift) * r[i];
                 }
             } else {
 #pragma unroll
@@ -274,137 +285,278 @@ __device__ __forceinline__ void dispatch_pass(const int tmpl, const int n1, cons
 }
 
 // ---- the kernel ----------------------------------------------------------------------------------
-// dynamic smem: psi[cap] | acc[cap] | mats[matcap] | FastTermDev
+// A CTA has 128 threads split into 128/gsize thread groups; every group owns one Smolyak term at a
+// time (persistent, static round-robin over the cost-sorted terms of its size class) and runs a
+// software pipeline built on cp.async (LDGSTS): while term i is being transformed, the packed-psi
+// gather of term i+1, the mapping slice of term i+2 and the descriptor/1-D matrices of term i+1 are
+// in flight, and V of term i lands in the (not yet used) acc buffer during the first B->G passes.
+//
+// dynamic smem per group:
+//   psi[2][cap] | acc[cap] | map[2][mapcap] | mats[2][matcap] | FastTermDev[2] | moff[2][2*EVR_MAXG]
+__device__ __forceinline__ void group_sync(const int gsize, const int group)
+{
+    if (gsize == 32) __syncwarp();
+    else if (gsize == 128) __syncthreads();
+    else asm volatile("bar.sync %0, %1;" ::"r"(group + 1), "r"(gsize) : "memory");
+}
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void cp_async4(void *dst, const void *src)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void *dst, const void *src)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async8_zfill(void *dst, const void *src, const bool valid)
+{
+    const int n = valid ? 8 : 0;       // src-size 0: the 8 destination bytes are zero-filled
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(smem_u32(dst)), "l"(src), "r"(n) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+struct GroupSmem {
+    double *psi[2], *acc, *mat[2];
+    int32_t *map[2];
+    FastTermDev *T[2];
+    int *moff[2];
+};
+
+// gather of one right-hand side of a term into a psi buffer (tabPackedBasis_TO_tabR_AT_iG), asynchronous
+__device__ __forceinline__ void issue_gather(double *dst, const int32_t *smap, const int nq, const int nb0,
+                                             const double *x, const long long nb, const int tid, const int gsize)
+{
+    for (int j = tid; j < nq; j += gsize) {
+        const int m = smap[j];
+        const long long src = (m > 0) ? (long long)(m - 1) : 0;
+        for (int c = 0; c < nb0; ++c) cp_async8_zfill(dst + c * nq + j, x + (long long)c * nb + src, m > 0);
+    }
+}
+
 __global__ void __launch_bounds__(128, 4)
-sg4_term_kernel_fast(const FastPlanDev P, const int npsi, const double *__restrict__ psi, double *__restrict__ Hpsi)
+sg4_term_kernel_fast(const FastPlanDev P, const FastClassDev Cc, const int npsi,
+                     const double *__restrict__ psi, double *__restrict__ Hpsi)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    double *s_psi = reinterpret_cast<double *>(smem_raw);
-    double *s_acc = s_psi + P.cap;
-    double *s_mat = s_acc + P.cap;
-    FastTermDev *s_T = reinterpret_cast<FastTermDev *>(s_mat + P.matcap);
-    __shared__ int s_moff[2 * EVR_MAXG];
-
+    const int gsize = Cc.gsize;
+    const int ngrp = 128 / gsize;
+    const int group = threadIdx.x / gsize;
+    const int tid = threadIdx.x - group * gsize;
+    const int cap = Cc.cap, mapcap = Cc.mapcap, matcap = P.matcap;
+    const size_t per_group = ((size_t)3 * cap + 2 * matcap) * sizeof(double) + (size_t)2 * mapcap * sizeof(int32_t) +
+                             2 * sizeof(FastTermDev) + 4 * EVR_MAXG * sizeof(int);
+    GroupSmem S;
+    {
+        unsigned char *q = smem_raw + per_group * group;
+        S.psi[0] = reinterpret_cast<double *>(q); S.psi[1] = S.psi[0] + cap; S.acc = S.psi[1] + cap;
+        S.mat[0] = S.acc + cap; S.mat[1] = S.mat[0] + matcap;
+        S.T[0] = reinterpret_cast<FastTermDev *>(S.mat[1] + matcap); S.T[1] = S.T[0] + 1;
+        S.map[0] = reinterpret_cast<int32_t *>(S.T[1] + 1); S.map[1] = S.map[0] + mapcap;
+        S.moff[0] = reinterpret_cast<int *>(S.map[1] + mapcap); S.moff[1] = S.moff[0] + 2 * EVR_MAXG;
+    }
     const int nb0 = P.nb0;
     const long long nvec = P.nb * nb0;
+    const int step = gridDim.x * ngrp;
+    const int it0 = blockIdx.x * ngrp + group;
+    if (it0 >= Cc.n_terms) return;            // whole group idle (groups never sync with each other, except gsize 128 = whole CTA)
+    const FastTermDev *terms = P.terms + Cc.term_begin;
+    const bool v_fused = (nb0 == 1);
 
-    for (int it = blockIdx.x; it < P.n_terms; it += gridDim.x) {
-        __syncthreads();
-        {   // term descriptor -> smem
-            const int *src = reinterpret_cast<const int *>(P.terms + it);
-            int *dst = reinterpret_cast<int *>(s_T);
-            for (int i = threadIdx.x; i < (int)(sizeof(FastTermDev) / sizeof(int)); i += blockDim.x) dst[i] = __ldg(src + i);
+    auto stage_desc_sync = [&](int slot, int it) {     // plain (blocking) descriptor load, prologue only
+        const int *src = reinterpret_cast<const int *>(terms + it);
+        int *dst = reinterpret_cast<int *>(S.T[slot]);
+        for (int i = tid; i < (int)(sizeof(FastTermDev) / sizeof(int)); i += gsize) dst[i] = __ldg(src + i);
+    };
+    auto issue_desc = [&](int slot, int it) {
+        const double *src = reinterpret_cast<const double *>(terms + it);
+        double *dst = reinterpret_cast<double *>(S.T[slot]);
+        for (int i = tid; i < (int)(sizeof(FastTermDev) / 8); i += gsize) cp_async8(dst + i, src + i);
+    };
+    auto issue_map = [&](int slot, long long map_off, int nq) {
+        const int32_t *src = P.map + map_off;
+        for (int j = tid; j < nq; j += gsize) cp_async4(S.map[slot] + j, src + j);
+    };
+    auto set_moff = [&](int slot) {                // by one thread, after the descriptor in 'slot' is visible
+        const FastTermDev *T = S.T[slot];
+        int off = 0;
+        for (int g = 0; g < T->ngroups; ++g) {
+            const int n1 = T->g[g].n1, n2 = T->g[g].n2;
+            S.moff[slot][2 * g] = off; off += 3 * n1 * n1;
+            S.moff[slot][2 * g + 1] = off; off += 3 * n2 * n2;
         }
-        __syncthreads();
-        const int G = s_T->ngroups, nq = s_T->nq;
-        if (threadIdx.x == 0) {   // smem offsets of each mode's [B|BTw|T] block
-            int off = 0;
-            for (int g = 0; g < G; ++g) {
-                const int n1 = s_T->g[g].n1, n2 = s_T->g[g].n2;
-                s_moff[2 * g] = off; off += 3 * n1 * n1;
-                s_moff[2 * g + 1] = off; off += 3 * n2 * n2;
-            }
+    };
+    auto issue_mats = [&](int slot) {              // needs S.T[slot] and S.moff[slot] visible
+        const FastTermDev *T = S.T[slot];
+        for (int g = 0; g < T->ngroups; ++g) {
+            const int n1 = T->g[g].n1, n2 = T->g[g].n2;
+            const double *src1 = P.mats + T->g[g].mat1, *src2 = P.mats + T->g[g].mat2;
+            double *d1 = S.mat[slot] + S.moff[slot][2 * g], *d2 = S.mat[slot] + S.moff[slot][2 * g + 1];
+            for (int i = tid; i < 3 * n1 * n1; i += gsize) cp_async8(d1 + i, src1 + i);
+            for (int i = tid; i < 3 * n2 * n2; i += gsize) cp_async8(d2 + i, src2 + i);
         }
-        __syncthreads();
-        for (int g = 0; g < G; ++g) {
-            const int n1 = s_T->g[g].n1, n2 = s_T->g[g].n2;
-            const double *src1 = P.mats + s_T->g[g].mat1, *src2 = P.mats + s_T->g[g].mat2;
-            double *d1 = s_mat + s_moff[2 * g], *d2 = s_mat + s_moff[2 * g + 1];
-            for (int i = threadIdx.x; i < 3 * n1 * n1; i += blockDim.x) d1[i] = __ldg(src1 + i);
-            for (int i = threadIdx.x; i < 3 * n2 * n2; i += blockDim.x) d2[i] = __ldg(src2 + i);
-        }
-        const int32_t *mp = P.map + s_T->map_off;
-        const double weight = s_T->weight, vshift = s_T->vshift;
-        const double *Vt = (P.has_V) ? P.V + s_T->grid_off : nullptr;
+    };
 
-        for (int ip = 0; ip < npsi; ++ip) {
-            const double *x = psi + (long long)ip * nvec;
+    // ---- prologue: term it0 fully staged, gather of its first RHS and map of the next term in flight
+    stage_desc_sync(0, it0);
+    group_sync(gsize, group);
+    if (tid == 0) set_moff(0);
+    issue_map(0, S.T[0]->map_off, S.T[0]->nq);
+    cp_async_commit();
+    cp_async_wait<0>();
+    group_sync(gsize, group);
+    issue_mats(0);
+    issue_gather(S.psi[0], S.map[0], S.T[0]->nq, nb0, psi, P.nb, tid, gsize);
+    cp_async_commit();                                            // [A]
+    cp_async_commit();                                            // [X] (empty)
+    if (S.T[0]->next_nq > 0) issue_map(1, S.T[0]->next_map_off, S.T[0]->next_nq);
+    cp_async_commit();                                            // [M]
+
+    int n_item = 0;
+    for (int it = it0; it < Cc.n_terms; it += step) {
+        const int ts = ((it - it0) / step) & 1;                   // term slot (descriptor, map, mats)
+        const bool has_next_term = (it + step < Cc.n_terms);
+        for (int ip = 0; ip < npsi; ++ip, ++n_item) {
+            const int ps = n_item & 1;                            // psi slot
+            const bool last_ip = (ip == npsi - 1);
+            // top: gather of this item ([A]) and the matrices ([X]) have landed; [M] may still be pending
+            cp_async_wait<1>();
+            group_sync(gsize, group);
+            const FastTermDev *T = S.T[ts];
+            const int G = T->ngroups, nq = T->nq;
+            const double weight = T->weight, vshift = T->vshift;
+            const double *Vt = (P.has_V) ? P.V + T->grid_off : nullptr;
+            double *s_psi = S.psi[ps], *s_acc = S.acc;
+            const double *s_mat = S.mat[ts];
+            const int *s_moff = S.moff[ts];
             double *y = Hpsi + (long long)ip * nvec;
-            // gather (tabPackedBasis_TO_tabR_AT_iG)
-            for (int j = threadIdx.x; j < nq; j += blockDim.x) {
-                const int m = __ldg(mp + j);
-                for (int c = 0; c < nb0; ++c)
-                    s_psi[c * nq + j] = (m > 0) ? __ldg(x + (long long)c * P.nb + (m - 1)) : 0.0;
-            }
-            __syncthreads();
-            PassArgs A;
-            A.psi = s_psi; A.acc = s_acc; A.nq = nq; A.nb0 = nb0; A.vshift = vshift;
-            const bool v_fused = (nb0 == 1);
-            if (G == 0) {
-                // every mode is 1x1: a single grid point per channel
-                if (threadIdx.x < nb0) s_acc[threadIdx.x] = vshift * s_psi[threadIdx.x] +
-                                                            ((v_fused && Vt) ? __ldg(Vt) * s_psi[threadIdx.x] : 0.0);
-                __syncthreads();
-            } else {
-                // B -> G on all but the last group (BDP_TO_GDP_OF_SmolyakRep)
-                for (int g = 0; g < G - 1; ++g) {
-                    const FastGroup &Gr = s_T->g[g];
-                    A.kind = PASS_XFORM; A.which = 0; A.stride = Gr.stride;
-                    A.m1 = s_mat + s_moff[2 * g]; A.m2 = s_mat + s_moff[2 * g + 1]; A.V = nullptr;
-                    A.fuse_g2b = 0; A.store_psi = 0;
-                    dispatch_pass(Gr.tmpl, Gr.n1, A);
-                    __syncthreads();
+            // [V]: V of this term -> acc buffer (read and overwritten element-wise by the LAST pass);
+            //      descriptor of the next term; L2 prefetch of the next term's V slice
+            if (v_fused && Vt)
+                for (int j = tid; j < nq; j += gsize) cp_async8(s_acc + j, Vt + j);
+            if (ip == 0 && has_next_term) {
+                issue_desc(ts ^ 1, it + step);
+                if (P.has_V) {
+                    const char *pv = reinterpret_cast<const char *>(P.V + T->next_grid_off);
+                    for (int b = tid * 128; b < T->next_nq * 8; b += gsize * 128) prefetch_l2(pv + b);
                 }
+                const char *pm = reinterpret_cast<const char *>(P.map + T->next2_map_off);
+                for (int b = tid * 128; b < T->next2_nq * 4; b += gsize * 128) prefetch_l2(pm + b);
+            }
+            cp_async_commit();                                    // [V]
+
+            PassArgs A;
+            A.psi = s_psi; A.acc = s_acc; A.nq = nq; A.nb0 = nb0; A.vshift = vshift; A.tid = tid; A.nthr = gsize;
+            int g_done = 0;
+            if (G >= 2) {   // first B -> G pass overlaps the landing of [M]
+                const FastGroup &Gr = T->g[0];
+                A.kind = PASS_XFORM; A.which = 0; A.stride = Gr.stride;
+                A.m1 = s_mat + s_moff[0]; A.m2 = s_mat + s_moff[1]; A.V = nullptr; A.fuse_g2b = 0; A.store_psi = 0;
+                dispatch_pass(Gr.tmpl, Gr.n1, A);
+                g_done = 1;
+            }
+            // [M] (map of the next term) has landed -> issue the gather of the next item
+            cp_async_wait<1>();
+            group_sync(gsize, group);
+            if (!last_ip) {
+                issue_gather(S.psi[ps ^ 1], S.map[ts], nq, nb0, psi + (long long)(ip + 1) * nvec, P.nb, tid, gsize);
+            } else if (has_next_term) {
+                issue_gather(S.psi[ps ^ 1], S.map[ts ^ 1], T->next_nq, nb0, psi, P.nb, tid, gsize);
+            }
+            cp_async_commit();                                    // [A]
+            if (G == 0) {
+                cp_async_wait<1>();                               // [V]
+                group_sync(gsize, group);
+                if (tid < nb0) {
+                    const double v0 = (v_fused && Vt) ? s_acc[tid] : 0.0;
+                    s_acc[tid] = (vshift + v0) * s_psi[tid];
+                }
+                group_sync(gsize, group);
+            } else {
+                for (int g = g_done; g < G - 1; ++g) {            // remaining B -> G (BDP_TO_GDP_OF_SmolyakRep)
+                    const FastGroup &Gr = T->g[g];
+                    A.kind = PASS_XFORM; A.which = 0; A.stride = Gr.stride;
+                    A.m1 = s_mat + s_moff[2 * g]; A.m2 = s_mat + s_moff[2 * g + 1]; A.V = nullptr; A.fuse_g2b = 0; A.store_psi = 0;
+                    dispatch_pass(Gr.tmpl, Gr.n1, A);
+                    group_sync(gsize, group);
+                }
+                cp_async_wait<1>();                               // [V] landed (and the next descriptor)
+                group_sync(gsize, group);
                 {   // last group: B -> G, (V+shift) psi, its kinetic part (, its G -> B when it is the only group)
                     const int g = G - 1;
-                    const FastGroup &Gr = s_T->g[g];
+                    const FastGroup &Gr = T->g[g];
                     A.kind = PASS_LAST; A.which = 0; A.stride = Gr.stride;
                     A.m1 = s_mat + s_moff[2 * g]; A.m2 = s_mat + s_moff[2 * g + 1];
-                    A.V = v_fused ? Vt : nullptr;
+                    A.V = (v_fused && Vt) ? s_acc : nullptr;
                     A.fuse_g2b = (G == 1 && v_fused) ? 1 : 0;
                     A.store_psi = (G > 1 || !v_fused) ? 1 : 0;
                     dispatch_pass(Gr.tmpl, Gr.n1, A);
-                    __syncthreads();
+                    group_sync(gsize, group);
                 }
             }
+            // [X]: matrices of the next term (its descriptor arrived with [V])
+            if (last_ip && has_next_term) {
+                if (tid == 0) set_moff(ts ^ 1);
+                group_sync(gsize, group);
+                issue_mats(ts ^ 1);
+            }
+            cp_async_commit();                                    // [X]
             if (!v_fused && Vt) {
                 // channel-coupling potential: acc(q,i) += sum_j V(q,i,j) psi(q,j)   (sub_OpPsi_SG4.f90:1521-1525)
-                for (int q = threadIdx.x; q < nq; q += blockDim.x) {
+                for (int q = tid; q < nq; q += gsize) {
                     double pj[EVR_MAXCH];
 #pragma unroll
                     for (int j = 0; j < EVR_MAXCH; ++j) if (j < nb0) pj[j] = s_psi[j * nq + q];
 #pragma unroll
                     for (int i = 0; i < EVR_MAXCH; ++i) if (i < nb0) {
-                        double s = s_acc[i * nq + q];
+                        double sacc = s_acc[i * nq + q];
 #pragma unroll
                         for (int j = 0; j < EVR_MAXCH; ++j) if (j < nb0)
-                            s = fma(__ldg(Vt + (long long)(i + nb0 * j) * P.NQ_local + q), pj[j], s);
-                        s_acc[i * nq + q] = s;
+                            sacc = fma(__ldg(Vt + (long long)(i + nb0 * j) * P.NQ_local + q), pj[j], sacc);
+                        s_acc[i * nq + q] = sacc;
                     }
                 }
-                __syncthreads();
+                group_sync(gsize, group);
             }
             if (G > 0) {
                 // kinetic parts of the other groups; the last one also transforms its group G -> B
                 for (int g = G - 2; g >= 0; --g) {
-                    const FastGroup &Gr = s_T->g[g];
+                    const FastGroup &Gr = T->g[g];
                     A.kind = PASS_KEO; A.which = 0; A.stride = Gr.stride;
                     A.m1 = s_mat + s_moff[2 * g]; A.m2 = s_mat + s_moff[2 * g + 1]; A.V = nullptr;
                     A.fuse_g2b = (g == 0) ? 1 : 0; A.store_psi = 0;
                     dispatch_pass(Gr.tmpl, Gr.n1, A);
-                    __syncthreads();
+                    group_sync(gsize, group);
                 }
                 // remaining G -> B (GDP_TO_BDP_OF_SmolyakRep)
                 const int g_first = (G == 1) ? (v_fused ? 1 : 0) : 1;
                 for (int g = g_first; g < G; ++g) {
-                    const FastGroup &Gr = s_T->g[g];
+                    const FastGroup &Gr = T->g[g];
                     A.kind = PASS_XFORM; A.which = 1; A.stride = Gr.stride;
-                    A.m1 = s_mat + s_moff[2 * g]; A.m2 = s_mat + s_moff[2 * g + 1]; A.V = nullptr;
-                    A.fuse_g2b = 0; A.store_psi = 0;
+                    A.m1 = s_mat + s_moff[2 * g]; A.m2 = s_mat + s_moff[2 * g + 1]; A.V = nullptr; A.fuse_g2b = 0; A.store_psi = 0;
                     dispatch_pass(Gr.tmpl, Gr.n1, A);
-                    __syncthreads();
+                    group_sync(gsize, group);
                 }
             }
-            // weighted scatter-add (tabR_AT_iG_TO_tabPackedBasis)
-            for (int j = threadIdx.x; j < nq; j += blockDim.x) {
-                const int m = __ldg(mp + j);
-                if (m > 0)
-                    for (int c = 0; c < nb0; ++c)
-                        atomicAdd(y + (long long)c * P.nb + (m - 1), weight * s_acc[c * nq + j]);
+            // weighted scatter-add (tabR_AT_iG_TO_tabPackedBasis); the mapping slice is still in smem
+            {
+                const int32_t *smap = S.map[ts];
+                for (int j = tid; j < nq; j += gsize) {
+                    const int m = smap[j];
+                    if (m > 0)
+                        for (int c = 0; c < nb0; ++c)
+                            atomicAdd(y + (long long)c * P.nb + (m - 1), weight * s_acc[c * nq + j]);
+                }
             }
-            __syncthreads();
+            group_sync(gsize, group);
+            // [M]: mapping slice of the term after next goes into the slot this term just released
+            if (last_ip && T->next2_nq > 0) issue_map(ts, T->next2_map_off, T->next2_nq);
+            cp_async_commit();                                    // [M]
         }
     }
+    cp_async_wait<0>();
 }
 
 } // namespace evr

@@ -61,8 +61,11 @@ struct evr_sg4_plan {
     int32_t *d_fmap = nullptr;
     double *d_fmats = nullptr, *d_fV = nullptr;
     evr::FastPlanDev fpd{};
-    size_t fast_smem = 0;
-    int fast_ctas = 0;
+    std::vector<double> h_cost;             // per local term
+    int n_classes = 0;
+    evr::FastClassDev fclass[3];
+    size_t fclass_smem[3] = {0, 0, 0};
+    int fclass_ctas[3] = {0, 0, 0};
     // device
     evr::TermDev *d_terms = nullptr;
     uint8_t *d_lev = nullptr;
@@ -192,6 +195,7 @@ extern "C" int evr_sg4_plan_create(evr_sg4_plan **out, int device,
     p->h_D1.assign(D1, D1 + og); p->h_D2.assign(D2, D2 + og);
     p->h_weight.assign(WeightSG, WeightSG + nb_SG);
     p->h_offB = offB; p->h_offG = offG;
+    p->h_cost = cost;
     p->order.resize(p->n_terms);
     std::iota(p->order.begin(), p->order.end(), 0);
     std::stable_sort(p->order.begin(), p->order.end(), [&](int a, int b) { return cost[a] > cost[b]; });
@@ -310,6 +314,16 @@ static int build_fast_path(evr_sg4_plan *p, int nb_Term, const int32_t *term_mod
             for (int e = 0; e < n * n; ++e) pool.push_back(c2[k] * d2[e] + c1[k] * d1[e]);
         }
     // per-term schedules + permutation to the internal layout
+    // size classes: how many threads cooperate on one term (tiles per pass ~ nq/9 .. nq/21)
+    auto class_of = [&](int t) { const int64_t sz = (int64_t)p->h_tab_nq[p->iG_begin + t] * nb0; return sz > 1024 ? 0 : (sz > 384 ? 1 : 2); };
+    static const int class_gsize[3] = {128, 64, 32};
+    std::vector<int> forder(p->n_terms);
+    std::iota(forder.begin(), forder.end(), 0);
+    std::stable_sort(forder.begin(), forder.end(), [&](int a, int b) {
+        const int ca = class_of(a), cb = class_of(b);
+        if (ca != cb) return ca < cb;
+        return p->h_cost[a] > p->h_cost[b];
+    });
     std::vector<evr::FastTermDev> fterms(p->n_terms);
     std::vector<int32_t> fmap((size_t)std::max<int64_t>(p->S_local, 1));
     std::vector<double> fV;
@@ -319,7 +333,7 @@ static int build_fast_path(evr_sg4_plan *p, int nb_Term, const int32_t *term_mod
 #pragma omp parallel for schedule(dynamic, 64) reduction(max:matcap)
     for (int w = 0; w < p->n_terms; ++w) {
         if (!ok) continue;
-        const int t = p->order[w], iG = p->iG_begin + t;
+        const int t = forder[w], iG = p->iG_begin + t;
         evr::FastTermDev &F = fterms[w];
         std::memset(&F, 0, sizeof(F));
         F.map_off = p->h_map_off[t]; F.grid_off = p->h_grid_off[t];
@@ -396,26 +410,56 @@ static int build_fast_path(evr_sg4_plan *p, int nb_Term, const int32_t *term_mod
     }
     if (!ok) return 0;
     if ((size_t)matcap * sizeof(double) > 48 * 1024) return 0;
-    int64_t cap = 1;
-    for (int t = 0; t < p->n_terms; ++t) cap = std::max<int64_t>(cap, p->h_tab_nq[p->iG_begin + t]);
-    cap *= nb0;
-    size_t smem = ((size_t)2 * cap + matcap) * sizeof(double) + sizeof(evr::FastTermDev);
-    if (smem > 200 * 1024) return 0;
-
+    // launch configuration per size class + "next term" prefetch links
+    CUDA_TRY(cudaFuncSetAttribute(evr::sg4_term_kernel_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    p->n_classes = 0;
+    {
+        int w0 = 0;
+        for (int c = 0; c < 3; ++c) {
+            int w1 = w0;
+            int64_t cap = 1, mapcap = 1;
+            while (w1 < p->n_terms && class_of(forder[w1]) == c) {
+                cap = std::max<int64_t>(cap, (int64_t)fterms[w1].nq * nb0);
+                mapcap = std::max<int64_t>(mapcap, (int64_t)fterms[w1].nq);
+                ++w1;
+            }
+            mapcap = (mapcap + 1) & ~(int64_t)1;      // keep the following buffers 8-byte aligned
+            if (w1 == w0) continue;
+            const int gsize = class_gsize[c], ngrp = 128 / gsize;
+            const size_t per_group = ((size_t)3 * cap + 2 * matcap) * sizeof(double) + (size_t)2 * mapcap * sizeof(int32_t) +
+                                     2 * sizeof(evr::FastTermDev) + 4 * EVR_MAXG * sizeof(int);
+            const size_t smem = per_group * ngrp;
+            if (smem > 200 * 1024) return 0;
+            int occ = 0;
+            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, evr::sg4_term_kernel_fast, 128, smem));
+            if (occ < 1) return 0;
+            const int n = w1 - w0;
+            const int ctas = std::max(1, std::min((n + ngrp - 1) / ngrp, p->sm_count * occ));
+            const int step = ctas * ngrp;
+            for (int w = w0; w < w1; ++w) {
+                evr::FastTermDev &F = fterms[w];
+                if (w + step < w1) { F.next_map_off = fterms[w + step].map_off; F.next_grid_off = fterms[w + step].grid_off; F.next_nq = fterms[w + step].nq; }
+                else { F.next_map_off = 0; F.next_grid_off = 0; F.next_nq = 0; }
+                if (w + 2 * step < w1) { F.next2_map_off = fterms[w + 2 * step].map_off; F.next2_nq = fterms[w + 2 * step].nq; }
+                else { F.next2_map_off = 0; F.next2_nq = 0; }
+            }
+            evr::FastClassDev &C = p->fclass[p->n_classes];
+            C.term_begin = w0; C.n_terms = n; C.gsize = gsize; C.cap = (int)cap; C.mapcap = (int)mapcap;
+            p->fclass_smem[p->n_classes] = smem; p->fclass_ctas[p->n_classes] = ctas;
+            ++p->n_classes;
+            w0 = w1;
+        }
+    }
     cudaFree(p->d_fterms); cudaFree(p->d_fmap); cudaFree(p->d_fmats); cudaFree(p->d_fV);
     p->d_fterms = nullptr; p->d_fmap = nullptr; p->d_fmats = nullptr; p->d_fV = nullptr;
     if (upload(&p->d_fterms, fterms.data(), fterms.size())) return 1;
     if (upload(&p->d_fmap, fmap.data(), fmap.size())) return 1;
     if (upload(&p->d_fmats, pool.data(), pool.size())) return 1;
     if (Vgrid && upload(&p->d_fV, fV.data(), fV.size())) return 1;
-    CUDA_TRY(cudaFuncSetAttribute(evr::sg4_term_kernel_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int occ = 0;
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, evr::sg4_term_kernel_fast, 128, smem));
-    if (occ < 1) return 0;
-    p->fast_smem = smem;
-    p->fast_ctas = std::max(1, std::min(p->n_terms, p->sm_count * occ));
+    int64_t cap = 1;
     evr::FastPlanDev &f = p->fpd;
     f.nb0 = nb0; f.n_terms = p->n_terms; f.cap = (int)cap; f.matcap = matcap; f.has_V = Vgrid ? 1 : 0;
+    (void)cap;
     f.nb = p->nb; f.NQ_local = p->NQ_local;
     f.terms = p->d_fterms; f.map = p->d_fmap; f.mats = p->d_fmats; f.V = p->d_fV;
     p->fast = true;
@@ -495,12 +539,16 @@ static int launch(evr_sg4_plan *p, int npsi, const double *d_psi, double *d_Hpsi
     const size_t bytes = (size_t)npsi * p->nb * p->nb0 * sizeof(double);
     CUDA_TRY(cudaMemsetAsync(d_Hpsi, 0, bytes, st));                 // reference zeroes OpPsi (:765)
     if (p->n_terms > 0) {
-        if (p->fast)
-            evr::sg4_term_kernel_fast<<<p->fast_ctas, 128, p->fast_smem, st>>>(p->fpd, npsi, d_psi, d_Hpsi);
-        else
+        if (p->fast) {
+            for (int c = 0; c < p->n_classes; ++c) {
+                evr::sg4_term_kernel_fast<<<p->fclass_ctas[c], 128, p->fclass_smem[c], st>>>(p->fpd, p->fclass[c], npsi, d_psi, d_Hpsi);
+                p->launches += 1;
+            }
+        } else {
             evr::sg4_term_kernel_generic<<<p->grid_ctas, 256, p->smem_bytes, st>>>(p->pd, npsi, d_psi, d_Hpsi);
+            p->launches += 1;
+        }
         CUDA_TRY(cudaGetLastError());
-        p->launches += 1;
     }
     return 0;
 }
@@ -550,8 +598,8 @@ extern "C" int64_t evr_sg4_plan_info(const evr_sg4_plan *p, int what)
         return p->S_local * nb0 * 8 * 2 + p->nb * nb0 * 8 * 2;
     case EVR_INFO_NQ_LOCAL: return p->NQ_local;
     case EVR_INFO_S_LOCAL: return p->S_local;
-    case EVR_INFO_SMEM_BYTES: return (int64_t)(p->fast ? p->fast_smem : p->smem_bytes);
-    case EVR_INFO_GRID_CTAS: return p->fast ? p->fast_ctas : p->grid_ctas;
+    case EVR_INFO_SMEM_BYTES: return (int64_t)(p->fast ? p->fclass_smem[0] : p->smem_bytes);
+    case EVR_INFO_GRID_CTAS: return p->fast ? p->fclass_ctas[0] : p->grid_ctas;
     case EVR_INFO_PATH: return p->fast ? 1 : 0;
     case EVR_INFO_FLOPS_NPSI1: return p->flops_npsi1;
     default: return -1;
