@@ -17,7 +17,8 @@
 //     kinetic pass also does its group's G->B, so a term with G groups makes 7G-2 shared-memory
 //     sweeps instead of ~7 per mode;
 //   * the term-local layout is permuted on the host (largest group fastest); mapping and V are
-//     stored in that order, so gather/scatter/V reads stay coalesced.
+//     stored in that order, so gather/scatter/V reads stay coalesced;
+//   * global traffic is decoupled from the arithmetic by a cp.async (LDGSTS) software pipeline.
 #pragma once
 #include <cstdint>
 #include "sg4_internal.h"
@@ -29,10 +30,11 @@ namespace evr {
 
 struct FastGroup {
     int stride;             // stride of the first mode of the group (second: stride*n1)
+    unsigned magic;         // floor(2^32/stride)+1 : exact t/stride by __umulhi for t*stride < 2^32 (stride > 1)
     unsigned short n1, n2;  // n2 = 0: single mode
     unsigned short tmpl;    // template id (0 = runtime single)
     unsigned short pad;
-    int mat1, mat2;         // offsets (doubles) of [B|BTw|T] blocks of mode 1 / 2 in the matrix pool
+    int mat1, mat2;         // offsets (doubles) of the [B|BTw|T] blocks of mode 1 / 2 in the matrix pool
 };
 
 struct FastTermDev {
@@ -41,7 +43,7 @@ struct FastTermDev {
     double vshift;          // sum_{1x1 modes} T(0,0) (+ constant (0,0) term)
     int nq, ngroups;
     long long next_map_off, next_grid_off;   // the term this thread group processes next
-    long long next2_map_off;                 // ... and the one after it (software pipeline, sg4_term_kernel_fast)
+    long long next2_map_off;                 // ... and the one after it (software pipeline)
     int next_nq, next2_nq;
     FastGroup g[EVR_MAXG];
 };
@@ -49,13 +51,15 @@ struct FastTermDev {
 struct FastClassDev {       // one launch per size class: terms [term_begin, term_begin+n_terms)
     int term_begin, n_terms;
     int gsize;              // threads cooperating on one term: 32, 64 or 128 (CTA = 128 threads)
+    int rt;                 // 1: runtime-size tiles (RT instantiation of the kernel)
     int cap;                // doubles per psi/acc buffer (max nq*nb0 of the class)
-    int mapcap;             // int32 per mapping buffer (max nq of the class)
+    int mapcap;             // int32 per mapping buffer (max nq of the class, even)
 };
 
 struct FastPlanDev {
-    int nb0, n_terms, cap, matcap;
-    int has_V;              // 1: variable (0,0) grid present
+    int nb0, n_terms, has_V;
+    int pool_len;           // doubles in the (de-duplicated) matrix pool
+    int dbg;                // experiment switches (EVR_SG4_DEBUG): 1 no scatter, 2 no gather, 4 no passes, 8 no V load
     long long nb, NQ_local;
     const FastTermDev *terms;
     const int32_t *map;     // permuted to the internal layout
@@ -65,234 +69,256 @@ struct FastPlanDev {
 
 // ---- tile primitives -------------------------------------------------------------------------
 // v[i2][i1] register tile; M column-major (n x n): out[q] = sum_b M[q + n*b] in[b]
+template <bool MS>
+__device__ __forceinline__ double ldm(const double *M, int i) { return MS ? M[i] : __ldg(M + i); }
+
 template <int N1, int N2>
-__device__ __forceinline__ void tile_load(double (&v)[N2][N1], const double *buf, int base, int stride)
+__device__ __forceinline__ void tile_load(double (&v)[N2][N1], const double *buf, int stride)
 {
 #pragma unroll
     for (int j = 0; j < N2; ++j)
 #pragma unroll
-        for (int i = 0; i < N1; ++i) v[j][i] = buf[base + stride * (i + N1 * j)];
+        for (int i = 0; i < N1; ++i) v[j][i] = buf[stride * (i + N1 * j)];
 }
 template <int N1, int N2>
-__device__ __forceinline__ void tile_store(const double (&v)[N2][N1], double *buf, int base, int stride)
+__device__ __forceinline__ void tile_store(const double (&v)[N2][N1], double *buf, int stride)
 {
 #pragma unroll
     for (int j = 0; j < N2; ++j)
 #pragma unroll
-        for (int i = 0; i < N1; ++i) buf[base + stride * (i + N1 * j)] = v[j][i];
+        for (int i = 0; i < N1; ++i) buf[stride * (i + N1 * j)] = v[j][i];
 }
-// v <- (M2 (x) M1) v
-template <int N1, int N2>
+// v <- (M2 (x) M1) v        (one matrix ROW is held in registers at a time)
+template <int N1, int N2, bool MS>
 __device__ __forceinline__ void tile_xform(double (&v)[N2][N1], const double *M1, const double *M2)
 {
-    if (N1 > 1) {
+    {
+        double t[N2][N1];
 #pragma unroll
-        for (int j = 0; j < N2; ++j) {
-            double t[N1];
+        for (int q = 0; q < N1; ++q) {
+            double mq[N1];
 #pragma unroll
-            for (int q = 0; q < N1; ++q) {
-                double s = 0.0;
+            for (int b = 0; b < N1; ++b) mq[b] = ldm<MS>(M1, q + N1 * b);
 #pragma unroll
-                for (int b = 0; b < N1; ++b) s = fma(M1[q + N1 * b], v[j][b], s);
-                t[q] = s;
+            for (int j = 0; j < N2; ++j) {
+                double s = mq[0] * v[j][0];
+#pragma unroll
+                for (int b = 1; b < N1; ++b) s = fma(mq[b], v[j][b], s);
+                t[j][q] = s;
             }
-#pragma unroll
-            for (int q = 0; q < N1; ++q) v[j][q] = t[q];
         }
+#pragma unroll
+        for (int j = 0; j < N2; ++j)
+#pragma unroll
+            for (int q = 0; q < N1; ++q) v[j][q] = t[j][q];
     }
     if (N2 > 1) {
+        double t[N2][N1];
 #pragma unroll
-        for (int i = 0; i < N1; ++i) {
-            double t[N2];
+        for (int q = 0; q < N2; ++q) {
+            double mq[N2];
 #pragma unroll
-            for (int q = 0; q < N2; ++q) {
-                double s = 0.0;
+            for (int b = 0; b < N2; ++b) mq[b] = ldm<MS>(M2, q + N2 * b);
 #pragma unroll
-                for (int b = 0; b < N2; ++b) s = fma(M2[q + N2 * b], v[b][i], s);
-                t[q] = s;
+            for (int i = 0; i < N1; ++i) {
+                double s = mq[0] * v[0][i];
+#pragma unroll
+                for (int b = 1; b < N2; ++b) s = fma(mq[b], v[b][i], s);
+                t[q][i] = s;
             }
-#pragma unroll
-            for (int q = 0; q < N2; ++q) v[q][i] = t[q];
         }
+#pragma unroll
+        for (int q = 0; q < N2; ++q)
+#pragma unroll
+            for (int i = 0; i < N1; ++i) v[q][i] = t[q][i];
     }
 }
 // a += (1 (x) T1 + T2 (x) 1) v
-template <int N1, int N2>
+template <int N1, int N2, bool MS>
 __device__ __forceinline__ void tile_keo(double (&a)[N2][N1], const double (&v)[N2][N1], const double *T1, const double *T2)
 {
 #pragma unroll
-    for (int j = 0; j < N2; ++j)
+    for (int q = 0; q < N1; ++q) {
+        double mq[N1];
 #pragma unroll
-        for (int q = 0; q < N1; ++q) {
+        for (int b = 0; b < N1; ++b) mq[b] = ldm<MS>(T1, q + N1 * b);
+#pragma unroll
+        for (int j = 0; j < N2; ++j) {
             double s = a[j][q];
 #pragma unroll
-            for (int b = 0; b < N1; ++b) s = fma(T1[q + N1 * b], v[j][b], s);
+            for (int b = 0; b < N1; ++b) s = fma(mq[b], v[j][b], s);
             a[j][q] = s;
         }
+    }
     if (N2 > 1) {
 #pragma unroll
-        for (int i = 0; i < N1; ++i)
+        for (int q = 0; q < N2; ++q) {
+            double mq[N2];
 #pragma unroll
-            for (int q = 0; q < N2; ++q) {
+            for (int b = 0; b < N2; ++b) mq[b] = ldm<MS>(T2, q + N2 * b);
+#pragma unroll
+            for (int i = 0; i < N1; ++i) {
                 double s = a[q][i];
 #pragma unroll
-                for (int b = 0; b < N2; ++b) s = fma(T2[q + N2 * b], v[b][i], s);
+                for (int b = 0; b < N2; ++b) s = fma(mq[b], v[b][i], s);
                 a[q][i] = s;
             }
+        }
     }
 }
 
-enum { PASS_XFORM = 0, PASS_LAST = 1, PASS_KEO = 2 };
+enum { PASS_B2G = 0, PASS_G2B = 1, PASS_LAST = 2, PASS_KEO = 3 };
 
 struct PassArgs {
-    double *psi, *acc;          // shared-memory buffers
-    const double *m1, *m2;      // shared-memory [B|BTw|T] blocks of the two modes
-    const double *V;            // shared memory copy of the term's V slice (nb0 == 1 fused) or nullptr
+    double *psi, *acc;          // shared-memory buffers of this item
+    const double *pool;         // matrix pool (shared memory when MS, else global)
+    int m1, m2;                 // offsets of the [B|BTw|T] blocks of the two modes in the pool
     double vshift;
     int nq, nb0, stride;
+    unsigned magic;
     int tid, nthr;              // thread index / count inside the group working on this term
-    int kind;                   // PASS_*
-    int which;                  // XFORM: 0 = B on psi, 1 = BTw on acc
+    int hasV;                   // LAST: V of the term sits in the acc buffer
     int fuse_g2b;               // LAST / KEO: also apply BTw of this group before storing acc
     int store_psi;              // LAST: psi needed later (G > 1)
 };
 
-template <int N1, int N2>
+__device__ __forceinline__ int tile_origin(const int t, const int stride, const unsigned magic, const int tile)
+{
+    if (stride == 1) return t * tile;
+    const int hi = (int)__umulhi((unsigned)t, magic);
+    return t + stride * (tile - 1) * hi;           // lo + stride*tile*hi with lo = t - hi*stride
+}
+
+template <int N1, int N2, int KIND, bool MS>
 __device__ __forceinline__ void run_pass(const PassArgs &A)
 {
-    constexpr int NN1 = N1 * N1, NN2 = N2 * N2;
-    const int tile = N1 * N2;
-    const int ntiles = A.nq / tile;
-    const int total = ntiles * A.nb0;
-    const double *B1 = A.m1, *W1 = A.m1 + NN1, *T1 = A.m1 + 2 * NN1;
-    const double *B2 = (N2 > 1) ? A.m2 : A.m1, *W2 = B2 + NN2, *T2 = B2 + 2 * NN2;
-    for (int t = A.tid; t < total; t += A.nthr) {
-        const int c = t / ntiles;
-        const int tt = t - c * ntiles;
-        const int hi = tt / A.stride;
-        const int lo = tt - hi * A.stride;
-        const int q0 = lo + A.stride * tile * hi;      // grid index of tile element (0,0)
-        const int base = c * A.nq + q0;
-        double v[N2][N1];
-        if (A.kind == PASS_XFORM) {
-            double *buf = A.which ? A.acc : A.psi;
-            tile_load<N1, N2>(v, buf, base, A.stride);
-            tile_xform<N1, N2>(v, A.which ? W1 : B1, A.which ? W2 : B2);
-            tile_store<N1, N2>(v, buf, base, A.stride);
-        } else if (A.kind == PASS_LAST) {
-            tile_load<N1, N2>(v, A.psi, base, A.stride);
-            tile_xform<N1, N2>(v, B1, B2);
-            if (A.store_psi) tile_store<N1, N2>(v, A.psi, base, A.stride);
-            double a[N2][N1];
-            if (A.V) {
+    constexpr int NN1 = N1 * N1, NN2 = N2 * N2, TILE = N1 * N2;
+    const int ntiles = A.nq / TILE;
+    const double *B1 = A.pool + A.m1, *W1 = B1 + NN1, *T1 = B1 + 2 * NN1;
+    const double *B2 = A.pool + ((N2 > 1) ? A.m2 : A.m1), *W2 = B2 + NN2, *T2 = B2 + 2 * NN2;
+    const int stride = A.stride;
+    for (int c = 0; c < A.nb0; ++c) {
+        double *psi = A.psi + c * A.nq, *acc = A.acc + c * A.nq;
+        for (int t = A.tid; t < ntiles; t += A.nthr) {
+            const int q0 = tile_origin(t, stride, A.magic, TILE);
+            double v[N2][N1];
+            if (KIND == PASS_B2G) {
+                tile_load<N1, N2>(v, psi + q0, stride);
+                tile_xform<N1, N2, MS>(v, B1, B2);
+                tile_store<N1, N2>(v, psi + q0, stride);
+            } else if (KIND == PASS_G2B) {
+                tile_load<N1, N2>(v, acc + q0, stride);
+                tile_xform<N1, N2, MS>(v, W1, W2);
+                tile_store<N1, N2>(v, acc + q0, stride);
+            } else if (KIND == PASS_LAST) {
+                tile_load<N1, N2>(v, psi + q0, stride);
+                tile_xform<N1, N2, MS>(v, B1, B2);
+                if (A.store_psi) tile_store<N1, N2>(v, psi + q0, stride);
+                double a[N2][N1];
+                if (A.hasV) {
+                    tile_load<N1, N2>(a, acc + q0, stride);
 #pragma unroll
-                for (int j = 0; j < N2; ++j)
+                    for (int j = 0; j < N2; ++j)
 #pragma unroll
-                    for (int i = 0; i < N1; ++i)
-                        a[j][i] = (A.V[q0 + A.stride * (i + N1 * j)] + A.vshift) * v[j][i];
+                        for (int i = 0; i < N1; ++i) a[j][i] = (a[j][i] + A.vshift) * v[j][i];
+                } else {
+#pragma unroll
+                    for (int j = 0; j < N2; ++j)
+#pragma unroll
+                        for (int i = 0; i < N1; ++i) a[j][i] = A.vshift * v[j][i];
+                }
+                tile_keo<N1, N2, MS>(a, v, T1, T2);
+                if (A.fuse_g2b) tile_xform<N1, N2, MS>(a, W1, W2);
+                tile_store<N1, N2>(a, acc + q0, stride);
             } else {
-#pragma unroll
-                for (int j = 0; j < N2; ++j)
-#pragma unroll
-                    for (int i = 0; i < N1; ++i) a[j][i] = A.vshift * v[j][i];
+                double a[N2][N1];
+                tile_load<N1, N2>(v, psi + q0, stride);
+                tile_load<N1, N2>(a, acc + q0, stride);
+                tile_keo<N1, N2, MS>(a, v, T1, T2);
+                if (A.fuse_g2b) tile_xform<N1, N2, MS>(a, W1, W2);
+                tile_store<N1, N2>(a, acc + q0, stride);
             }
-            tile_keo<N1, N2>(a, v, T1, T2);
-            if (A.fuse_g2b) tile_xform<N1, N2>(a, W1, W2);
-            tile_store<N1, N2>(a, A.acc, base, A.stride);
-        } else {
-            double a[N2][N1];
-            tile_load<N1, N2>(v, A.psi, base, A.stride);
-            tile_load<N1, N2>(a, A.acc, base, A.stride);
-            tile_keo<N1, N2>(a, v, T1, T2);
-            if (A.fuse_g2b) tile_xform<N1, N2>(a, W1, W2);
-            tile_store<N1, N2>(a, A.acc, base, A.stride);
         }
     }
 }
 
 // runtime-size single mode (n <= EVR_RT_NMAX): same passes with guarded, unrolled register arrays
-__device__ __noinline__ void run_pass_rt(const PassArgs &A, const int n)
+template <bool MS>
+__device__ __forceinline__ void run_pass_rt(const PassArgs &A, const int kind, const int n)
 {
+    const double *m1 = A.pool + A.m1;
     const int nn = n * n;
     const int ntiles = A.nq / n;
-    const int total = ntiles * A.nb0;
-    const double *B1 = A.m1, *W1 = A.m1 + nn, *T1 = A.m1 + 2 * nn;
-    for (int t = A.tid; t < total; t += A.nthr) {
-        const int c = t / ntiles;
-        const int tt = t - c * ntiles;
-        const int hi = tt / A.stride;
-        const int lo = tt - hi * A.stride;
-        const int q0 = lo + A.stride * n * hi;
-        const int base = c * A.nq + q0;
-        double v[EVR_RT_NMAX], a[EVR_RT_NMAX], r[EVR_RT_NMAX];
-        auto matvec = [&](const double *M, const double (&x)[EVR_RT_NMAX], double (&y)[EVR_RT_NMAX], bool accum) {
+    const double *B1 = m1, *W1 = m1 + nn, *T1 = m1 + 2 * nn;
+    for (int c = 0; c < A.nb0; ++c) {
+        double *psi = A.psi + c * A.nq, *acc = A.acc + c * A.nq;
+        for (int t = A.tid; t < ntiles; t += A.nthr) {
+            const int q0 = tile_origin(t, A.stride, A.magic, n);
+            double v[EVR_RT_NMAX], a[EVR_RT_NMAX], r[EVR_RT_NMAX];
+            auto matvec = [&](const double *M, const double (&x)[EVR_RT_NMAX], double (&y)[EVR_RT_NMAX], bool accum) {
 #pragma unroll
-            for (int q = 0; q < EVR_RT_NMAX; ++q) if (q < n) {
-                double s = accum ? y[q] : 0.0;
+                for (int q = 0; q < EVR_RT_NMAX; ++q) if (q < n) {
+                    double s = accum ? y[q] : 0.0;
 #pragma unroll
-                for (int b = 0; b < EVR_RT_NMAX; ++b) if (b < n) s = fma(M[q + n * b], x[b], s);
-                y[q] = s;
-            }
-        };
-        if (A.kind == PASS_XFORM) {
-            double *buf = A.which ? A.acc : A.psi;
-#pragma unroll
-            for (int i = 0; i < EVR_RT_NMAX; ++i) if (i < n) v[i] = buf[base + A.stride * i];
-            matvec(A.which ? W1 : B1, v, r, false);
-#pragma unroll
-            for (int i = 0; i < EVR_RT_NMAX; ++i) if (i < n) buf[base + A.stride * i] = r[i];
-        } else {
-#pragma unroll
-            for (int i = 0; i < EVR_RT_NMAX; ++i) if (i < n) v[i] = A.psi[base + A.stride * i];
-            if (A.kind == PASS_LAST) {
-                matvec(B1, v, r, false);
-#pragma unroll
-                for (int i = 0; i < EVR_RT_NMAX; ++i) if (i < n) {
-                    v[i] = r[i];
-                    if (A.store_psi) A.psi[base + A.stride * i] = r[i];
-                    a[i] = ((A.V ? A.V[q0 + A.stride * i] : 0.0) + A.vshift) * r[i];
+                    for (int b = 0; b < EVR_RT_NMAX; ++b) if (b < n) s = fma(ldm<MS>(M, q + n * b), x[b], s);
+                    y[q] = s;
                 }
+            };
+            if (kind == PASS_B2G || kind == PASS_G2B) {
+                double *buf = (kind == PASS_G2B) ? acc : psi;
+#pragma unroll
+                for (int i = 0; i < EVR_RT_NMAX; ++i) if (i < n) v[i] = buf[q0 + A.stride * i];
+                matvec((kind == PASS_G2B) ? W1 : B1, v, r, false);
+#pragma unroll
+                for (int i = 0; i < EVR_RT_NMAX; ++i) if (i < n) buf[q0 + A.stride * i] = r[i];
             } else {
 #pragma unroll
-                for (int i = 0; i < EVR_RT_NMAX; ++i) if (i < n) a[i] = A.acc[base + A.stride * i];
-            }
-            matvec(T1, v, a, true);
-            if (A.fuse_g2b) {
-                matvec(W1, a, r, false);
+                for (int i = 0; i < EVR_RT_NMAX; ++i) if (i < n) v[i] = psi[q0 + A.stride * i];
+                if (kind == PASS_LAST) {
+                    matvec(B1, v, r, false);
 #pragma unroll
-                for (int i = 0; i < EVR_RT_NMAX; ++i) if (i < n) A.acc[base + A.stride * i] = r[i];
-            } else {
+                    for (int i = 0; i < EVR_RT_NMAX; ++i) if (i < n) {
+                        v[i] = r[i];
+                        if (A.store_psi) psi[q0 + A.stride * i] = r[i];
+                        a[i] = ((A.hasV ? acc[q0 + A.stride * i] : 0.0) + A.vshift) * r[i];
+                    }
+                } else {
 #pragma unroll
-                for (int i = 0; i < EVR_RT_NMAX; ++i) if (i < n) A.acc[base + A.stride * i] = a[i];
+                    for (int i = 0; i < EVR_RT_NMAX; ++i) if (i < n) a[i] = acc[q0 + A.stride * i];
+                }
+                matvec(T1, v, a, true);
+                if (A.fuse_g2b) {
+                    matvec(W1, a, r, false);
+#pragma unroll
+                    for (int i = 0; i < EVR_RT_NMAX; ++i) if (i < n) acc[q0 + A.stride * i] = r[i];
+                } else {
+#pragma unroll
+                    for (int i = 0; i < EVR_RT_NMAX; ++i) if (i < n) acc[q0 + A.stride * i] = a[i];
+                }
             }
         }
     }
 }
 
 // template ids (host side uses the same table, sg4_plan.cu: fast_template_id)
-#define EVR_TMPL_LIST(X) \
-    X(1, 2, 1) X(2, 3, 1) X(3, 4, 1) X(4, 5, 1) X(5, 7, 1) X(6, 9, 1) \
-    X(7, 2, 2) X(8, 2, 3) X(9, 3, 3) X(10, 3, 5) X(11, 3, 7) X(12, 2, 5) X(13, 3, 4)
+#define EVR_TMPL_LIST(X) X(1, 3, 1) X(2, 5, 1) X(3, 7, 1) X(4, 3, 3) X(5, 3, 5) X(6, 3, 7) X(7, 2, 1) X(8, 2, 3) X(9, 4, 1)
 
+template <int KIND, bool MS, bool RT>
 __device__ __forceinline__ void dispatch_pass(const int tmpl, const int n1, const PassArgs &A)
 {
-    switch (tmpl) {
-#define X(id, a, b) case id: run_pass<a, b>(A); break;
-        EVR_TMPL_LIST(X)
+    if (RT) {                    // terms with a mode size that has no template: runtime-size single-mode tiles only
+        run_pass_rt<MS>(A, KIND, n1);
+    } else {
+        switch (tmpl) {
+#define X(id, a, b) case id: run_pass<a, b, KIND, MS>(A); break;
+            EVR_TMPL_LIST(X)
 #undef X
-    default: run_pass_rt(A, n1); break;
+        default: break;          // unreachable: the plan sends such terms to the RT instantiation
+        }
     }
 }
 
-// ---- the kernel ----------------------------------------------------------------------------------
-// A CTA has 128 threads split into 128/gsize thread groups; every group owns one Smolyak term at a
-// time (persistent, static round-robin over the cost-sorted terms of its size class) and runs a
-// software pipeline built on cp.async (LDGSTS): while term i is being transformed, the packed-psi
-// gather of term i+1, the mapping slice of term i+2 and the descriptor/1-D matrices of term i+1 are
-// in flight, and V of term i lands in the (not yet used) acc buffer during the first B->G passes.
-//
-// dynamic smem per group:
-//   psi[2][cap] | acc[cap] | map[2][mapcap] | mats[2][matcap] | FastTermDev[2] | moff[2][2*EVR_MAXG]
+// ---- cp.async helpers ------------------------------------------------------------------------
 __device__ __forceinline__ void group_sync(const int gsize, const int group)
 {
     if (gsize == 32) __syncwarp();
@@ -318,24 +344,16 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-struct GroupSmem {
-    double *psi[2], *acc, *mat[2];
-    int32_t *map[2];
-    FastTermDev *T[2];
-    int *moff[2];
-};
-
-// gather of one right-hand side of a term into a psi buffer (tabPackedBasis_TO_tabR_AT_iG), asynchronous
-__device__ __forceinline__ void issue_gather(double *dst, const int32_t *smap, const int nq, const int nb0,
-                                             const double *x, const long long nb, const int tid, const int gsize)
-{
-    for (int j = tid; j < nq; j += gsize) {
-        const int m = smap[j];
-        const long long src = (m > 0) ? (long long)(m - 1) : 0;
-        for (int c = 0; c < nb0; ++c) cp_async8_zfill(dst + c * nq + j, x + (long long)c * nb + src, m > 0);
-    }
-}
-
+// ---- the kernel ----------------------------------------------------------------------------------
+// A CTA has 128 threads split into 128/gsize thread groups; every group owns one Smolyak term at a
+// time (persistent, static round-robin over the cost-sorted terms of its size class) and runs a
+// software pipeline built on cp.async (LDGSTS): while item n (= one right-hand side of one term) is
+// being transformed, the packed-psi gather of item n+1, the mapping slice of term i+2 and the
+// descriptor of term i+1 are in flight, and V of term i lands in the (not yet used) acc buffer during
+// the first B->G pass.  cp.async groups are committed in the fixed order [V] [A] [M] per item.
+//
+// dynamic smem:  pool[pool_len] (MS only) | per group: psi[2][cap] | acc[cap] | FastTermDev[2] | map[2][mapcap]
+template <bool MS, bool RT>
 __global__ void __launch_bounds__(128, 4)
 sg4_term_kernel_fast(const FastPlanDev P, const FastClassDev Cc, const int npsi,
                      const double *__restrict__ psi, double *__restrict__ Hpsi)
@@ -345,99 +363,85 @@ sg4_term_kernel_fast(const FastPlanDev P, const FastClassDev Cc, const int npsi,
     const int ngrp = 128 / gsize;
     const int group = threadIdx.x / gsize;
     const int tid = threadIdx.x - group * gsize;
-    const int cap = Cc.cap, mapcap = Cc.mapcap, matcap = P.matcap;
-    const size_t per_group = ((size_t)3 * cap + 2 * matcap) * sizeof(double) + (size_t)2 * mapcap * sizeof(int32_t) +
-                             2 * sizeof(FastTermDev) + 4 * EVR_MAXG * sizeof(int);
-    GroupSmem S;
-    {
-        unsigned char *q = smem_raw + per_group * group;
-        S.psi[0] = reinterpret_cast<double *>(q); S.psi[1] = S.psi[0] + cap; S.acc = S.psi[1] + cap;
-        S.mat[0] = S.acc + cap; S.mat[1] = S.mat[0] + matcap;
-        S.T[0] = reinterpret_cast<FastTermDev *>(S.mat[1] + matcap); S.T[1] = S.T[0] + 1;
-        S.map[0] = reinterpret_cast<int32_t *>(S.T[1] + 1); S.map[1] = S.map[0] + mapcap;
-        S.moff[0] = reinterpret_cast<int *>(S.map[1] + mapcap); S.moff[1] = S.moff[0] + 2 * EVR_MAXG;
+    const int cap = Cc.cap, mapcap = Cc.mapcap;
+    const int pool_doubles = MS ? P.pool_len : 0;
+    const size_t per_group = (size_t)3 * cap * sizeof(double) + 2 * sizeof(FastTermDev) + (size_t)2 * mapcap * sizeof(int32_t);
+    double *s_pool = reinterpret_cast<double *>(smem_raw);
+    unsigned char *gbase = smem_raw + (size_t)pool_doubles * sizeof(double) + per_group * group;
+    double *s_psi0 = reinterpret_cast<double *>(gbase);
+    double *s_acc = s_psi0 + 2 * cap;
+    FastTermDev *s_T0 = reinterpret_cast<FastTermDev *>(s_acc + cap);
+    int32_t *s_map0 = reinterpret_cast<int32_t *>(s_T0 + 2);
+
+    if (MS) {   // the whole (de-duplicated) 1-D matrix pool lives in shared memory for the kernel's lifetime
+        for (int i = threadIdx.x; i < P.pool_len; i += 128) s_pool[i] = __ldg(P.mats + i);
+        __syncthreads();
     }
+    const double *mats = MS ? s_pool : P.mats;
+
     const int nb0 = P.nb0;
     const long long nvec = P.nb * nb0;
     const int step = gridDim.x * ngrp;
     const int it0 = blockIdx.x * ngrp + group;
-    if (it0 >= Cc.n_terms) return;            // whole group idle (groups never sync with each other, except gsize 128 = whole CTA)
+    if (it0 >= Cc.n_terms) return;            // idle group (groups never sync with each other; gsize 128 = whole CTA)
     const FastTermDev *terms = P.terms + Cc.term_begin;
     const bool v_fused = (nb0 == 1);
 
-    auto stage_desc_sync = [&](int slot, int it) {     // plain (blocking) descriptor load, prologue only
-        const int *src = reinterpret_cast<const int *>(terms + it);
-        int *dst = reinterpret_cast<int *>(S.T[slot]);
-        for (int i = tid; i < (int)(sizeof(FastTermDev) / sizeof(int)); i += gsize) dst[i] = __ldg(src + i);
-    };
-    auto issue_desc = [&](int slot, int it) {
-        const double *src = reinterpret_cast<const double *>(terms + it);
-        double *dst = reinterpret_cast<double *>(S.T[slot]);
-        for (int i = tid; i < (int)(sizeof(FastTermDev) / 8); i += gsize) cp_async8(dst + i, src + i);
-    };
     auto issue_map = [&](int slot, long long map_off, int nq) {
         const int32_t *src = P.map + map_off;
-        for (int j = tid; j < nq; j += gsize) cp_async4(S.map[slot] + j, src + j);
+        int32_t *dst = s_map0 + slot * mapcap;
+        for (int j = tid; j < nq; j += gsize) cp_async4(dst + j, src + j);
     };
-    auto set_moff = [&](int slot) {                // by one thread, after the descriptor in 'slot' is visible
-        const FastTermDev *T = S.T[slot];
-        int off = 0;
-        for (int g = 0; g < T->ngroups; ++g) {
-            const int n1 = T->g[g].n1, n2 = T->g[g].n2;
-            S.moff[slot][2 * g] = off; off += 3 * n1 * n1;
-            S.moff[slot][2 * g + 1] = off; off += 3 * n2 * n2;
-        }
-    };
-    auto issue_mats = [&](int slot) {              // needs S.T[slot] and S.moff[slot] visible
-        const FastTermDev *T = S.T[slot];
-        for (int g = 0; g < T->ngroups; ++g) {
-            const int n1 = T->g[g].n1, n2 = T->g[g].n2;
-            const double *src1 = P.mats + T->g[g].mat1, *src2 = P.mats + T->g[g].mat2;
-            double *d1 = S.mat[slot] + S.moff[slot][2 * g], *d2 = S.mat[slot] + S.moff[slot][2 * g + 1];
-            for (int i = tid; i < 3 * n1 * n1; i += gsize) cp_async8(d1 + i, src1 + i);
-            for (int i = tid; i < 3 * n2 * n2; i += gsize) cp_async8(d2 + i, src2 + i);
+    auto issue_gather = [&](int pslot, int mslot, int nq, const double *x) {   // tabPackedBasis_TO_tabR_AT_iG
+        double *dst = s_psi0 + pslot * cap;
+        const int32_t *smap = s_map0 + mslot * mapcap;
+        for (int j = tid; j < nq; j += gsize) {
+            const int m = (P.dbg & 2) ? 0 : smap[j];
+            const long long src = (m > 0) ? (long long)(m - 1) : 0;
+            for (int c = 0; c < nb0; ++c) cp_async8_zfill(dst + c * nq + j, x + (long long)c * P.nb + src, m > 0);
         }
     };
 
-    // ---- prologue: term it0 fully staged, gather of its first RHS and map of the next term in flight
-    stage_desc_sync(0, it0);
+    // ---- prologue: descriptor + map of the first term, then its first gather and the next map in flight
+    {
+        const int *src = reinterpret_cast<const int *>(terms + it0);
+        int *dst = reinterpret_cast<int *>(s_T0);
+        for (int i = tid; i < (int)(sizeof(FastTermDev) / sizeof(int)); i += gsize) dst[i] = __ldg(src + i);
+    }
     group_sync(gsize, group);
-    if (tid == 0) set_moff(0);
-    issue_map(0, S.T[0]->map_off, S.T[0]->nq);
+    issue_map(0, s_T0->map_off, s_T0->nq);
     cp_async_commit();
     cp_async_wait<0>();
     group_sync(gsize, group);
-    issue_mats(0);
-    issue_gather(S.psi[0], S.map[0], S.T[0]->nq, nb0, psi, P.nb, tid, gsize);
+    issue_gather(0, 0, s_T0->nq, psi);
     cp_async_commit();                                            // [A]
-    cp_async_commit();                                            // [X] (empty)
-    if (S.T[0]->next_nq > 0) issue_map(1, S.T[0]->next_map_off, S.T[0]->next_nq);
+    if (s_T0->next_nq > 0) issue_map(1, s_T0->next_map_off, s_T0->next_nq);
     cp_async_commit();                                            // [M]
 
-    int n_item = 0;
-    for (int it = it0; it < Cc.n_terms; it += step) {
-        const int ts = ((it - it0) / step) & 1;                   // term slot (descriptor, map, mats)
+    int n_item = 0, ts = 0;
+    for (int it = it0; it < Cc.n_terms; it += step, ts ^= 1) {
         const bool has_next_term = (it + step < Cc.n_terms);
         for (int ip = 0; ip < npsi; ++ip, ++n_item) {
             const int ps = n_item & 1;                            // psi slot
             const bool last_ip = (ip == npsi - 1);
-            // top: gather of this item ([A]) and the matrices ([X]) have landed; [M] may still be pending
+            // top: the gather of this item ([A]) has landed; [M] may still be pending
             cp_async_wait<1>();
             group_sync(gsize, group);
-            const FastTermDev *T = S.T[ts];
-            const int G = T->ngroups, nq = T->nq;
-            const double weight = T->weight, vshift = T->vshift;
-            const double *Vt = (P.has_V) ? P.V + T->grid_off : nullptr;
-            double *s_psi = S.psi[ps], *s_acc = S.acc;
-            const double *s_mat = S.mat[ts];
-            const int *s_moff = S.moff[ts];
-            double *y = Hpsi + (long long)ip * nvec;
+            const FastTermDev *T = s_T0 + ts;
+            const int G = (P.dbg & 4) ? 0 : T->ngroups, nq = T->nq;
+            double *s_psi = s_psi0 + ps * cap;
+            const int32_t *smap = s_map0 + ts * mapcap;
+            const bool hasV = v_fused && P.has_V;
             // [V]: V of this term -> acc buffer (read and overwritten element-wise by the LAST pass);
-            //      descriptor of the next term; L2 prefetch of the next term's V slice
-            if (v_fused && Vt)
+            //      descriptor of the next term; L2 prefetch of the next term's V and the map after next
+            if (hasV && !(P.dbg & 8)) {
+                const double *Vt = P.V + T->grid_off;
                 for (int j = tid; j < nq; j += gsize) cp_async8(s_acc + j, Vt + j);
+            }
             if (ip == 0 && has_next_term) {
-                issue_desc(ts ^ 1, it + step);
+                const double *src = reinterpret_cast<const double *>(terms + it + step);
+                double *dst = reinterpret_cast<double *>(s_T0 + (ts ^ 1));
+                for (int i = tid; i < (int)(sizeof(FastTermDev) / 8); i += gsize) cp_async8(dst + i, src + i);
                 if (P.has_V) {
                     const char *pv = reinterpret_cast<const char *>(P.V + T->next_grid_off);
                     for (int b = tid * 128; b < T->next_nq * 8; b += gsize * 128) prefetch_l2(pv + b);
@@ -448,63 +452,49 @@ sg4_term_kernel_fast(const FastPlanDev P, const FastClassDev Cc, const int npsi,
             cp_async_commit();                                    // [V]
 
             PassArgs A;
-            A.psi = s_psi; A.acc = s_acc; A.nq = nq; A.nb0 = nb0; A.vshift = vshift; A.tid = tid; A.nthr = gsize;
+            A.psi = s_psi; A.acc = s_acc; A.nq = nq; A.nb0 = nb0; A.vshift = T->vshift; A.tid = tid; A.nthr = gsize;
+            A.hasV = 0; A.fuse_g2b = 0; A.store_psi = 0; A.pool = mats;
+            auto set_group = [&](int g) {
+                const FastGroup &Gr = T->g[g];
+                A.stride = Gr.stride; A.magic = Gr.magic; A.m1 = Gr.mat1; A.m2 = Gr.mat2;
+            };
             int g_done = 0;
-            if (G >= 2) {   // first B -> G pass overlaps the landing of [M]
-                const FastGroup &Gr = T->g[0];
-                A.kind = PASS_XFORM; A.which = 0; A.stride = Gr.stride;
-                A.m1 = s_mat + s_moff[0]; A.m2 = s_mat + s_moff[1]; A.V = nullptr; A.fuse_g2b = 0; A.store_psi = 0;
-                dispatch_pass(Gr.tmpl, Gr.n1, A);
+            if (G >= 2) {   // first B -> G pass overlaps the landing of [M]   (BDP_TO_GDP_OF_SmolyakRep)
+                set_group(0);
+                dispatch_pass<PASS_B2G, MS, RT>(T->g[0].tmpl, T->g[0].n1, A);
                 g_done = 1;
             }
-            // [M] (map of the next term) has landed -> issue the gather of the next item
+            // [M] (mapping slice of the next term) has landed -> issue the gather of the next item
             cp_async_wait<1>();
             group_sync(gsize, group);
-            if (!last_ip) {
-                issue_gather(S.psi[ps ^ 1], S.map[ts], nq, nb0, psi + (long long)(ip + 1) * nvec, P.nb, tid, gsize);
-            } else if (has_next_term) {
-                issue_gather(S.psi[ps ^ 1], S.map[ts ^ 1], T->next_nq, nb0, psi, P.nb, tid, gsize);
-            }
+            if (!last_ip) issue_gather(ps ^ 1, ts, nq, psi + (long long)(ip + 1) * nvec);
+            else if (has_next_term) issue_gather(ps ^ 1, ts ^ 1, T->next_nq, psi);
             cp_async_commit();                                    // [A]
             if (G == 0) {
                 cp_async_wait<1>();                               // [V]
                 group_sync(gsize, group);
-                if (tid < nb0) {
-                    const double v0 = (v_fused && Vt) ? s_acc[tid] : 0.0;
-                    s_acc[tid] = (vshift + v0) * s_psi[tid];
-                }
+                if (tid < nb0) s_acc[tid] = (T->vshift + (hasV ? s_acc[tid] : 0.0)) * s_psi[tid];
                 group_sync(gsize, group);
             } else {
-                for (int g = g_done; g < G - 1; ++g) {            // remaining B -> G (BDP_TO_GDP_OF_SmolyakRep)
-                    const FastGroup &Gr = T->g[g];
-                    A.kind = PASS_XFORM; A.which = 0; A.stride = Gr.stride;
-                    A.m1 = s_mat + s_moff[2 * g]; A.m2 = s_mat + s_moff[2 * g + 1]; A.V = nullptr; A.fuse_g2b = 0; A.store_psi = 0;
-                    dispatch_pass(Gr.tmpl, Gr.n1, A);
+                for (int g = g_done; g < G - 1; ++g) {            // remaining B -> G
+                    set_group(g);
+                    dispatch_pass<PASS_B2G, MS, RT>(T->g[g].tmpl, T->g[g].n1, A);
                     group_sync(gsize, group);
                 }
                 cp_async_wait<1>();                               // [V] landed (and the next descriptor)
                 group_sync(gsize, group);
-                {   // last group: B -> G, (V+shift) psi, its kinetic part (, its G -> B when it is the only group)
-                    const int g = G - 1;
-                    const FastGroup &Gr = T->g[g];
-                    A.kind = PASS_LAST; A.which = 0; A.stride = Gr.stride;
-                    A.m1 = s_mat + s_moff[2 * g]; A.m2 = s_mat + s_moff[2 * g + 1];
-                    A.V = (v_fused && Vt) ? s_acc : nullptr;
-                    A.fuse_g2b = (G == 1 && v_fused) ? 1 : 0;
-                    A.store_psi = (G > 1 || !v_fused) ? 1 : 0;
-                    dispatch_pass(Gr.tmpl, Gr.n1, A);
-                    group_sync(gsize, group);
-                }
-            }
-            // [X]: matrices of the next term (its descriptor arrived with [V])
-            if (last_ip && has_next_term) {
-                if (tid == 0) set_moff(ts ^ 1);
+                // last group: B -> G, (V+shift) psi, its kinetic part (, its G -> B when it is the only group)
+                set_group(G - 1);
+                A.hasV = hasV ? 1 : 0;
+                A.fuse_g2b = (G == 1 && v_fused) ? 1 : 0;
+                A.store_psi = (G > 1 || !v_fused) ? 1 : 0;
+                dispatch_pass<PASS_LAST, MS, RT>(T->g[G - 1].tmpl, T->g[G - 1].n1, A);
+                A.hasV = 0; A.store_psi = 0;
                 group_sync(gsize, group);
-                issue_mats(ts ^ 1);
             }
-            cp_async_commit();                                    // [X]
-            if (!v_fused && Vt) {
+            if (!v_fused && P.has_V) {
                 // channel-coupling potential: acc(q,i) += sum_j V(q,i,j) psi(q,j)   (sub_OpPsi_SG4.f90:1521-1525)
+                const double *Vt = P.V + T->grid_off;
                 for (int q = tid; q < nq; q += gsize) {
                     double pj[EVR_MAXCH];
 #pragma unroll
@@ -523,28 +513,26 @@ sg4_term_kernel_fast(const FastPlanDev P, const FastClassDev Cc, const int npsi,
             if (G > 0) {
                 // kinetic parts of the other groups; the last one also transforms its group G -> B
                 for (int g = G - 2; g >= 0; --g) {
-                    const FastGroup &Gr = T->g[g];
-                    A.kind = PASS_KEO; A.which = 0; A.stride = Gr.stride;
-                    A.m1 = s_mat + s_moff[2 * g]; A.m2 = s_mat + s_moff[2 * g + 1]; A.V = nullptr;
-                    A.fuse_g2b = (g == 0) ? 1 : 0; A.store_psi = 0;
-                    dispatch_pass(Gr.tmpl, Gr.n1, A);
+                    set_group(g);
+                    A.fuse_g2b = (g == 0) ? 1 : 0;
+                    dispatch_pass<PASS_KEO, MS, RT>(T->g[g].tmpl, T->g[g].n1, A);
                     group_sync(gsize, group);
                 }
+                A.fuse_g2b = 0;
                 // remaining G -> B (GDP_TO_BDP_OF_SmolyakRep)
                 const int g_first = (G == 1) ? (v_fused ? 1 : 0) : 1;
                 for (int g = g_first; g < G; ++g) {
-                    const FastGroup &Gr = T->g[g];
-                    A.kind = PASS_XFORM; A.which = 1; A.stride = Gr.stride;
-                    A.m1 = s_mat + s_moff[2 * g]; A.m2 = s_mat + s_moff[2 * g + 1]; A.V = nullptr; A.fuse_g2b = 0; A.store_psi = 0;
-                    dispatch_pass(Gr.tmpl, Gr.n1, A);
+                    set_group(g);
+                    dispatch_pass<PASS_G2B, MS, RT>(T->g[g].tmpl, T->g[g].n1, A);
                     group_sync(gsize, group);
                 }
             }
             // weighted scatter-add (tabR_AT_iG_TO_tabPackedBasis); the mapping slice is still in smem
             {
-                const int32_t *smap = S.map[ts];
+                const double weight = T->weight;
+                double *y = Hpsi + (long long)ip * nvec;
                 for (int j = tid; j < nq; j += gsize) {
-                    const int m = smap[j];
+                    const int m = (P.dbg & 1) ? 0 : smap[j];
                     if (m > 0)
                         for (int c = 0; c < nb0; ++c)
                             atomicAdd(y + (long long)c * P.nb + (m - 1), weight * s_acc[c * nq + j]);

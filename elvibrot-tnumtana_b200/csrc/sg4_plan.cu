@@ -15,6 +15,7 @@
 #include <cstdio>
 #include <cstring>
 #include <cstdlib>
+#include <map>
 #include <numeric>
 #include <string>
 #include <vector>
@@ -63,9 +64,10 @@ struct evr_sg4_plan {
     evr::FastPlanDev fpd{};
     std::vector<double> h_cost;             // per local term
     int n_classes = 0;
-    evr::FastClassDev fclass[3];
-    size_t fclass_smem[3] = {0, 0, 0};
-    int fclass_ctas[3] = {0, 0, 0};
+    bool fast_pool_in_smem = false;
+    evr::FastClassDev fclass[6];
+    size_t fclass_smem[6] = {0, 0, 0, 0, 0, 0};
+    int fclass_ctas[6] = {0, 0, 0, 0, 0, 0};
     // device
     evr::TermDev *d_terms = nullptr;
     uint8_t *d_lev = nullptr;
@@ -300,23 +302,46 @@ static int build_fast_path(evr_sg4_plan *p, int nb_Term, const int32_t *term_mod
             if (m1 == m2) c2[k] += c; else c1[k] += c;
         }
     }
-    // matrix pool [B|BTw|T] per (k,L)
+    // matrix pool [B|BTw|T] per (k,L), identical blocks stored once (e.g. 12 equal Hm modes)
     std::vector<int> moff(nT);
     std::vector<double> pool;
-    for (int k = 0; k < D; ++k)
-        for (int L = 0; L <= LG; ++L) {
-            const int i = k * (LG + 1) + L, n = p->h_nq_of[i];
-            moff[i] = (int)pool.size();
-            const double *Bm = p->h_B.data() + p->h_offB[i], *Wm = p->h_BTw.data() + p->h_offB[i];
-            const double *d1 = p->h_D1.data() + p->h_offG[i], *d2 = p->h_D2.data() + p->h_offG[i];
-            pool.insert(pool.end(), Bm, Bm + n * n);
-            pool.insert(pool.end(), Wm, Wm + n * n);
-            for (int e = 0; e < n * n; ++e) pool.push_back(c2[k] * d2[e] + c1[k] * d1[e]);
-        }
+    {
+        std::map<std::vector<double>, int> seen;
+        for (int k = 0; k < D; ++k)
+            for (int L = 0; L <= LG; ++L) {
+                const int i = k * (LG + 1) + L, n = p->h_nq_of[i];
+                const double *Bm = p->h_B.data() + p->h_offB[i], *Wm = p->h_BTw.data() + p->h_offB[i];
+                const double *d1 = p->h_D1.data() + p->h_offG[i], *d2 = p->h_D2.data() + p->h_offG[i];
+                std::vector<double> blk;
+                blk.reserve((size_t)3 * n * n);
+                blk.insert(blk.end(), Bm, Bm + n * n);
+                blk.insert(blk.end(), Wm, Wm + n * n);
+                for (int e = 0; e < n * n; ++e) blk.push_back(c2[k] * d2[e] + c1[k] * d1[e]);
+                auto itf = seen.find(blk);
+                if (itf != seen.end()) { moff[i] = itf->second; continue; }
+                moff[i] = (int)pool.size();
+                seen.emplace(blk, moff[i]);
+                pool.insert(pool.end(), blk.begin(), blk.end());
+            }
+    }
+    const bool pool_in_smem = pool.size() * sizeof(double) <= 24 * 1024;
     // per-term schedules + permutation to the internal layout
     // size classes: how many threads cooperate on one term (tiles per pass ~ nq/9 .. nq/21)
-    auto class_of = [&](int t) { const int64_t sz = (int64_t)p->h_tab_nq[p->iG_begin + t] * nb0; return sz > 1024 ? 0 : (sz > 384 ? 1 : 2); };
-    static const int class_gsize[3] = {128, 64, 32};
+    // a term whose active mode sizes all have single-mode templates uses the templated kernel; any other size
+    // (<= EVR_RT_NMAX) sends the whole term to the runtime-size instantiation (classes 3..5)
+    std::vector<char> term_rt(p->n_terms, 0);
+    for (int t = 0; t < p->n_terms; ++t) {
+        const int iG = p->iG_begin + t;
+        for (int k = 0; k < D; ++k) {
+            const int n = p->h_nq_of[k * (LG + 1) + p->h_tab_l[(size_t)iG * D + k]];
+            if (n > 1 && fast_template_id(n, 0) == 0) { term_rt[t] = 1; if (n > EVR_RT_NMAX) return 0; }
+        }
+    }
+    auto class_of = [&](int t) {
+        const int64_t sz = (int64_t)p->h_tab_nq[p->iG_begin + t] * nb0;
+        return (sz > 1024 ? 0 : (sz > 384 ? 1 : 2)) + (term_rt[t] ? 3 : 0);
+    };
+    static const int class_gsize[6] = {128, 64, 32, 128, 64, 32};
     std::vector<int> forder(p->n_terms);
     std::iota(forder.begin(), forder.end(), 0);
     std::stable_sort(forder.begin(), forder.end(), [&](int a, int b) {
@@ -328,9 +353,8 @@ static int build_fast_path(evr_sg4_plan *p, int nb_Term, const int32_t *term_mod
     std::vector<int32_t> fmap((size_t)std::max<int64_t>(p->S_local, 1));
     std::vector<double> fV;
     if (Vgrid) fV.resize((size_t)nb0 * nb0 * std::max<int64_t>(p->NQ_local, 1));
-    int matcap = 1;
     bool ok = true;
-#pragma omp parallel for schedule(dynamic, 64) reduction(max:matcap)
+#pragma omp parallel for schedule(dynamic, 64)
     for (int w = 0; w < p->n_terms; ++w) {
         if (!ok) continue;
         const int t = forder[w], iG = p->iG_begin + t;
@@ -357,7 +381,7 @@ static int build_fast_path(evr_sg4_plan *p, int nb_Term, const int32_t *term_mod
         std::vector<Grp> grp;
         int lo = 0, hi = (int)act.size() - 1;
         while (lo <= hi) {
-            if (lo < hi && fast_pair_supported(act[lo].n, act[hi].n)) { grp.push_back({lo, hi}); ++lo; --hi; }
+            if (!term_rt[t] && lo < hi && fast_pair_supported(act[lo].n, act[hi].n)) { grp.push_back({lo, hi}); ++lo; --hi; }
             else { grp.push_back({hi, -1}); --hi; }
         }
         auto gsize = [&](const Grp &g) { return act[g.a1].n * (g.a2 >= 0 ? act[g.a2].n : 1); };
@@ -367,28 +391,28 @@ static int build_fast_path(evr_sg4_plan *p, int nb_Term, const int32_t *term_mod
         F.weight = wgt; F.vshift = shift;
         // internal mode order and strides
         std::vector<int> in_n, in_ref;          // per internal mode: size, reference stride
-        int stride = 1, mats = 0;
+        int stride = 1;
         for (size_t g = 0; g < grp.size(); ++g) {
             const Act &A1 = act[grp[g].a1];
             evr::FastGroup &Gd = F.g[g];
             Gd.stride = stride;
+            Gd.magic = (stride > 1) ? (unsigned)((((uint64_t)1) << 32) / (uint64_t)stride + 1) : 0u;
             Gd.n1 = (unsigned short)A1.n;
             const int l1 = p->h_tab_l[(size_t)iG * D + A1.k];
             Gd.mat1 = moff[A1.k * (LG + 1) + l1];
             in_n.push_back(A1.n); in_ref.push_back(A1.refstride);
-            stride *= A1.n; mats += 3 * A1.n * A1.n;
+            stride *= A1.n;
             if (grp[g].a2 >= 0) {
                 const Act &A2 = act[grp[g].a2];
                 Gd.n2 = (unsigned short)A2.n;
                 const int l2 = p->h_tab_l[(size_t)iG * D + A2.k];
                 Gd.mat2 = moff[A2.k * (LG + 1) + l2];
                 in_n.push_back(A2.n); in_ref.push_back(A2.refstride);
-                stride *= A2.n; mats += 3 * A2.n * A2.n;
+                stride *= A2.n;
             } else { Gd.n2 = 0; Gd.mat2 = Gd.mat1; }
-            Gd.tmpl = (unsigned short)fast_template_id(Gd.n1, Gd.n2);
-            if (Gd.tmpl == 0 && (Gd.n2 != 0 || Gd.n1 > EVR_RT_NMAX)) ok = false;
+            Gd.tmpl = term_rt[t] ? 0 : (unsigned short)fast_template_id(Gd.n1, Gd.n2);
+            if (!term_rt[t] && Gd.tmpl == 0) ok = false;
         }
-        matcap = std::max(matcap, mats);
         // permutation: internal index q' -> reference index q (odometer over internal modes)
         const int nm = (int)in_n.size();
         std::vector<int> idx(nm, 0);
@@ -409,13 +433,15 @@ static int build_fast_path(evr_sg4_plan *p, int nb_Term, const int32_t *term_mod
         }
     }
     if (!ok) return 0;
-    if ((size_t)matcap * sizeof(double) > 48 * 1024) return 0;
     // launch configuration per size class + "next term" prefetch links
-    CUDA_TRY(cudaFuncSetAttribute(evr::sg4_term_kernel_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CUDA_TRY(cudaFuncSetAttribute(evr::sg4_term_kernel_fast<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CUDA_TRY(cudaFuncSetAttribute(evr::sg4_term_kernel_fast<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CUDA_TRY(cudaFuncSetAttribute(evr::sg4_term_kernel_fast<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CUDA_TRY(cudaFuncSetAttribute(evr::sg4_term_kernel_fast<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     p->n_classes = 0;
     {
         int w0 = 0;
-        for (int c = 0; c < 3; ++c) {
+        for (int c = 0; c < 6; ++c) {
             int w1 = w0;
             int64_t cap = 1, mapcap = 1;
             while (w1 < p->n_terms && class_of(forder[w1]) == c) {
@@ -426,12 +452,15 @@ static int build_fast_path(evr_sg4_plan *p, int nb_Term, const int32_t *term_mod
             mapcap = (mapcap + 1) & ~(int64_t)1;      // keep the following buffers 8-byte aligned
             if (w1 == w0) continue;
             const int gsize = class_gsize[c], ngrp = 128 / gsize;
-            const size_t per_group = ((size_t)3 * cap + 2 * matcap) * sizeof(double) + (size_t)2 * mapcap * sizeof(int32_t) +
-                                     2 * sizeof(evr::FastTermDev) + 4 * EVR_MAXG * sizeof(int);
-            const size_t smem = per_group * ngrp;
+            const size_t per_group = (size_t)3 * cap * sizeof(double) + 2 * sizeof(evr::FastTermDev) + (size_t)2 * mapcap * sizeof(int32_t);
+            const size_t smem = per_group * ngrp + (pool_in_smem ? pool.size() * sizeof(double) : 0);
             if (smem > 200 * 1024) return 0;
             int occ = 0;
-            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, evr::sg4_term_kernel_fast, 128, smem));
+            const bool rt = (c >= 3);
+            if (pool_in_smem && !rt) CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, evr::sg4_term_kernel_fast<true, false>, 128, smem));
+            else if (!pool_in_smem && !rt) CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, evr::sg4_term_kernel_fast<false, false>, 128, smem));
+            else if (pool_in_smem) CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, evr::sg4_term_kernel_fast<true, true>, 128, smem));
+            else CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, evr::sg4_term_kernel_fast<false, true>, 128, smem));
             if (occ < 1) return 0;
             const int n = w1 - w0;
             const int ctas = std::max(1, std::min((n + ngrp - 1) / ngrp, p->sm_count * occ));
@@ -444,7 +473,7 @@ static int build_fast_path(evr_sg4_plan *p, int nb_Term, const int32_t *term_mod
                 else { F.next2_map_off = 0; F.next2_nq = 0; }
             }
             evr::FastClassDev &C = p->fclass[p->n_classes];
-            C.term_begin = w0; C.n_terms = n; C.gsize = gsize; C.cap = (int)cap; C.mapcap = (int)mapcap;
+            C.term_begin = w0; C.n_terms = n; C.gsize = gsize; C.rt = rt ? 1 : 0; C.cap = (int)cap; C.mapcap = (int)mapcap;
             p->fclass_smem[p->n_classes] = smem; p->fclass_ctas[p->n_classes] = ctas;
             ++p->n_classes;
             w0 = w1;
@@ -456,10 +485,10 @@ static int build_fast_path(evr_sg4_plan *p, int nb_Term, const int32_t *term_mod
     if (upload(&p->d_fmap, fmap.data(), fmap.size())) return 1;
     if (upload(&p->d_fmats, pool.data(), pool.size())) return 1;
     if (Vgrid && upload(&p->d_fV, fV.data(), fV.size())) return 1;
-    int64_t cap = 1;
     evr::FastPlanDev &f = p->fpd;
-    f.nb0 = nb0; f.n_terms = p->n_terms; f.cap = (int)cap; f.matcap = matcap; f.has_V = Vgrid ? 1 : 0;
-    (void)cap;
+    f.nb0 = nb0; f.n_terms = p->n_terms; f.has_V = Vgrid ? 1 : 0; f.pool_len = (int)pool.size();
+    p->fast_pool_in_smem = pool_in_smem;
+    f.dbg = getenv("EVR_SG4_DEBUG") ? atoi(getenv("EVR_SG4_DEBUG")) : 0;
     f.nb = p->nb; f.NQ_local = p->NQ_local;
     f.terms = p->d_fterms; f.map = p->d_fmap; f.mats = p->d_fmats; f.V = p->d_fV;
     p->fast = true;
@@ -541,7 +570,15 @@ static int launch(evr_sg4_plan *p, int npsi, const double *d_psi, double *d_Hpsi
     if (p->n_terms > 0) {
         if (p->fast) {
             for (int c = 0; c < p->n_classes; ++c) {
-                evr::sg4_term_kernel_fast<<<p->fclass_ctas[c], 128, p->fclass_smem[c], st>>>(p->fpd, p->fclass[c], npsi, d_psi, d_Hpsi);
+                const bool ms = p->fast_pool_in_smem, rt = p->fclass[c].rt != 0;
+                if (ms && !rt)
+                    evr::sg4_term_kernel_fast<true, false><<<p->fclass_ctas[c], 128, p->fclass_smem[c], st>>>(p->fpd, p->fclass[c], npsi, d_psi, d_Hpsi);
+                else if (!ms && !rt)
+                    evr::sg4_term_kernel_fast<false, false><<<p->fclass_ctas[c], 128, p->fclass_smem[c], st>>>(p->fpd, p->fclass[c], npsi, d_psi, d_Hpsi);
+                else if (ms)
+                    evr::sg4_term_kernel_fast<true, true><<<p->fclass_ctas[c], 128, p->fclass_smem[c], st>>>(p->fpd, p->fclass[c], npsi, d_psi, d_Hpsi);
+                else
+                    evr::sg4_term_kernel_fast<false, true><<<p->fclass_ctas[c], 128, p->fclass_smem[c], st>>>(p->fpd, p->fclass[c], npsi, d_psi, d_Hpsi);
                 p->launches += 1;
             }
         } else {
