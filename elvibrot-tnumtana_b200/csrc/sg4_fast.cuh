@@ -50,10 +50,10 @@ struct FastTermDev {
 
 struct FastClassDev {       // one launch per size class: terms [term_begin, term_begin+n_terms)
     int term_begin, n_terms;
-    int gsize;              // threads cooperating on one term: 32, 64 or 128 (CTA = 128 threads)
+    int gsize;              // threads cooperating on one term: 32, 64 or 128
     int rt;                 // 1: runtime-size tiles (RT instantiation of the kernel)
     int cap;                // doubles per psi/acc buffer (max nq*nb0 of the class)
-    int mapcap;             // int32 per mapping buffer (max nq of the class, even)
+    int cta_threads;        // threads per CTA = groups per CTA * gsize (<= 768)
 };
 
 struct FastPlanDev {
@@ -301,7 +301,8 @@ __device__ __forceinline__ void run_pass_rt(const PassArgs &A, const int kind, c
 }
 
 // template ids (host side uses the same table, sg4_plan.cu: fast_template_id)
-#define EVR_TMPL_LIST(X) X(1, 3, 1) X(2, 5, 1) X(3, 7, 1) X(4, 3, 3) X(5, 3, 5) X(6, 3, 7) X(7, 2, 1) X(8, 2, 3) X(9, 4, 1)
+#define EVR_TMPL_LIST(X) X(1, 3, 1) X(2, 5, 1) X(3, 7, 1) X(4, 3, 3) X(7, 2, 1) X(8, 2, 3) X(9, 4, 1) X(10, 2, 2) \
+    X(11, 9, 1) X(12, 11, 1) X(13, 13, 1) X(14, 15, 1) X(15, 6, 1) X(16, 8, 1)
 
 template <int KIND, bool MS, bool RT>
 __device__ __forceinline__ void dispatch_pass(const int tmpl, const int n1, const PassArgs &A)
@@ -318,63 +319,50 @@ __device__ __forceinline__ void dispatch_pass(const int tmpl, const int n1, cons
     }
 }
 
-// ---- cp.async helpers ------------------------------------------------------------------------
+// ---- the kernel ----------------------------------------------------------------------------------
+// One persistent CTA per SM with up to 768 threads, split into thread groups of gsize = 32/64/128
+// threads; every group owns one Smolyak term at a time (static round-robin over the cost-sorted terms
+// of its size class) and synchronises only with itself (named barriers / __syncwarp).  Global-memory
+// latency of one group's gather/scatter is hidden by the arithmetic of the other groups on the SM;
+// the next term's mapping and V slices are pulled into L2 one term ahead (prefetch.global.L2).
+//
+// dynamic smem:  pool[pool_len] (MS only) | per group: psi[cap] | acc[cap] | FastTermDev[2]
 __device__ __forceinline__ void group_sync(const int gsize, const int group)
 {
     if (gsize == 32) __syncwarp();
-    else if (gsize == 128) __syncthreads();
     else asm volatile("bar.sync %0, %1;" ::"r"(group + 1), "r"(gsize) : "memory");
 }
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
-__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void cp_async4(void *dst, const void *src)
-{
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
-}
 __device__ __forceinline__ void cp_async8(void *dst, const void *src)
 {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
 }
-__device__ __forceinline__ void cp_async8_zfill(void *dst, const void *src, const bool valid)
-{
-    const int n = valid ? 8 : 0;       // src-size 0: the 8 destination bytes are zero-filled
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(smem_u32(dst)), "l"(src), "r"(n) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void cp_async_commit_wait_all() { asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory"); }
 
-// ---- the kernel ----------------------------------------------------------------------------------
-// A CTA has 128 threads split into 128/gsize thread groups; every group owns one Smolyak term at a
-// time (persistent, static round-robin over the cost-sorted terms of its size class) and runs a
-// software pipeline built on cp.async (LDGSTS): while item n (= one right-hand side of one term) is
-// being transformed, the packed-psi gather of item n+1, the mapping slice of term i+2 and the
-// descriptor of term i+1 are in flight, and V of term i lands in the (not yet used) acc buffer during
-// the first B->G pass.  cp.async groups are committed in the fixed order [V] [A] [M] per item.
-//
-// dynamic smem:  pool[pool_len] (MS only) | per group: psi[2][cap] | acc[cap] | FastTermDev[2] | map[2][mapcap]
+#define EVR_FAST_MAX_THREADS 768
+#define EVR_GS_MAX 18       // max elements per thread in gather/scatter: ceil(cap_class / gsize) <= 18 (plan checks)
+
 template <bool MS, bool RT>
-__global__ void __launch_bounds__(128, 4)
+__global__ void __launch_bounds__(EVR_FAST_MAX_THREADS, 1)
 sg4_term_kernel_fast(const FastPlanDev P, const FastClassDev Cc, const int npsi,
                      const double *__restrict__ psi, double *__restrict__ Hpsi)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int gsize = Cc.gsize;
-    const int ngrp = 128 / gsize;
+    const int ngrp = blockDim.x / gsize;
     const int group = threadIdx.x / gsize;
     const int tid = threadIdx.x - group * gsize;
-    const int cap = Cc.cap, mapcap = Cc.mapcap;
+    const int cap = Cc.cap;
     const int pool_doubles = MS ? P.pool_len : 0;
-    const size_t per_group = (size_t)3 * cap * sizeof(double) + 2 * sizeof(FastTermDev) + (size_t)2 * mapcap * sizeof(int32_t);
+    const size_t per_group = (size_t)2 * cap * sizeof(double) + 2 * sizeof(FastTermDev);
     double *s_pool = reinterpret_cast<double *>(smem_raw);
     unsigned char *gbase = smem_raw + (size_t)pool_doubles * sizeof(double) + per_group * group;
-    double *s_psi0 = reinterpret_cast<double *>(gbase);
-    double *s_acc = s_psi0 + 2 * cap;
+    double *s_psi = reinterpret_cast<double *>(gbase);
+    double *s_acc = s_psi + cap;
     FastTermDev *s_T0 = reinterpret_cast<FastTermDev *>(s_acc + cap);
-    int32_t *s_map0 = reinterpret_cast<int32_t *>(s_T0 + 2);
 
     if (MS) {   // the whole (de-duplicated) 1-D matrix pool lives in shared memory for the kernel's lifetime
-        for (int i = threadIdx.x; i < P.pool_len; i += 128) s_pool[i] = __ldg(P.mats + i);
+        for (int i = threadIdx.x; i < P.pool_len; i += blockDim.x) s_pool[i] = __ldg(P.mats + i);
         __syncthreads();
     }
     const double *mats = MS ? s_pool : P.mats;
@@ -382,74 +370,71 @@ sg4_term_kernel_fast(const FastPlanDev P, const FastClassDev Cc, const int npsi,
     const int nb0 = P.nb0;
     const long long nvec = P.nb * nb0;
     const int step = gridDim.x * ngrp;
-    const int it0 = blockIdx.x * ngrp + group;
-    if (it0 >= Cc.n_terms) return;            // idle group (groups never sync with each other; gsize 128 = whole CTA)
     const FastTermDev *terms = P.terms + Cc.term_begin;
     const bool v_fused = (nb0 == 1);
+    const bool hasV = v_fused && P.has_V;
 
-    auto issue_map = [&](int slot, long long map_off, int nq) {
-        const int32_t *src = P.map + map_off;
-        int32_t *dst = s_map0 + slot * mapcap;
-        for (int j = tid; j < nq; j += gsize) cp_async4(dst + j, src + j);
-    };
-    auto issue_gather = [&](int pslot, int mslot, int nq, const double *x) {   // tabPackedBasis_TO_tabR_AT_iG
-        double *dst = s_psi0 + pslot * cap;
-        const int32_t *smap = s_map0 + mslot * mapcap;
-        for (int j = tid; j < nq; j += gsize) {
-            const int m = (P.dbg & 2) ? 0 : smap[j];
-            const long long src = (m > 0) ? (long long)(m - 1) : 0;
-            for (int c = 0; c < nb0; ++c) cp_async8_zfill(dst + c * nq + j, x + (long long)c * P.nb + src, m > 0);
-        }
-    };
-
-    // ---- prologue: descriptor + map of the first term, then its first gather and the next map in flight
-    {
-        const int *src = reinterpret_cast<const int *>(terms + it0);
-        int *dst = reinterpret_cast<int *>(s_T0);
-        for (int i = tid; i < (int)(sizeof(FastTermDev) / sizeof(int)); i += gsize) dst[i] = __ldg(src + i);
+    const int it_first = blockIdx.x * ngrp + group;
+    if (it_first < Cc.n_terms) {   // first descriptor of this group
+        const double *src = reinterpret_cast<const double *>(terms + it_first);
+        double *dst = reinterpret_cast<double *>(s_T0);
+        for (int i = tid; i < (int)(sizeof(FastTermDev) / 8); i += gsize) cp_async8(dst + i, src + i);
     }
-    group_sync(gsize, group);
-    issue_map(0, s_T0->map_off, s_T0->nq);
-    cp_async_commit();
-    cp_async_wait<0>();
-    group_sync(gsize, group);
-    issue_gather(0, 0, s_T0->nq, psi);
-    cp_async_commit();                                            // [A]
-    if (s_T0->next_nq > 0) issue_map(1, s_T0->next_map_off, s_T0->next_nq);
-    cp_async_commit();                                            // [M]
+    int ts = 0;
+    for (int it = it_first; it < Cc.n_terms; it += step, ts ^= 1) {
+        cp_async_commit_wait_all();            // descriptor of this term has landed (issued one term ago)
+        group_sync(gsize, group);
+        if (it + step < Cc.n_terms) {          // descriptor of the next term -> other slot, asynchronously
+            const double *src = reinterpret_cast<const double *>(terms + it + step);
+            double *dst = reinterpret_cast<double *>(s_T0 + (ts ^ 1));
+            for (int i = tid; i < (int)(sizeof(FastTermDev) / 8); i += gsize) cp_async8(dst + i, src + i);
+        }
+        const FastTermDev *T = s_T0 + ts;
+        const int G = (P.dbg & 4) ? 0 : T->ngroups, nq = T->nq;
+        if (T->next_nq > 0) {   // pull the next term's mapping / V slices and descriptor into L2
+            const char *pm = reinterpret_cast<const char *>(P.map + T->next_map_off);
+            for (int b = tid * 128; b < T->next_nq * 4; b += gsize * 128) prefetch_l2(pm + b);
+            if (P.has_V) {
+                const char *pv = reinterpret_cast<const char *>(P.V + T->next_grid_off);
+                for (int b = tid * 128; b < T->next_nq * 8; b += gsize * 128) prefetch_l2(pv + b);
+            }
+        }
+        const int32_t *mp = P.map + T->map_off;
+        const double *Vt = P.has_V ? P.V + T->grid_off : nullptr;
 
-    int n_item = 0, ts = 0;
-    for (int it = it0; it < Cc.n_terms; it += step, ts ^= 1) {
-        const bool has_next_term = (it + step < Cc.n_terms);
-        for (int ip = 0; ip < npsi; ++ip, ++n_item) {
-            const int ps = n_item & 1;                            // psi slot
-            const bool last_ip = (ip == npsi - 1);
-            // top: the gather of this item ([A]) has landed; [M] may still be pending
-            cp_async_wait<1>();
-            group_sync(gsize, group);
-            const FastTermDev *T = s_T0 + ts;
-            const int G = (P.dbg & 4) ? 0 : T->ngroups, nq = T->nq;
-            double *s_psi = s_psi0 + ps * cap;
-            const int32_t *smap = s_map0 + ts * mapcap;
-            const bool hasV = v_fused && P.has_V;
-            // [V]: V of this term -> acc buffer (read and overwritten element-wise by the LAST pass);
-            //      descriptor of the next term; L2 prefetch of the next term's V and the map after next
-            if (hasV && !(P.dbg & 8)) {
-                const double *Vt = P.V + T->grid_off;
-                for (int j = tid; j < nq; j += gsize) cp_async8(s_acc + j, Vt + j);
-            }
-            if (ip == 0 && has_next_term) {
-                const double *src = reinterpret_cast<const double *>(terms + it + step);
-                double *dst = reinterpret_cast<double *>(s_T0 + (ts ^ 1));
-                for (int i = tid; i < (int)(sizeof(FastTermDev) / 8); i += gsize) cp_async8(dst + i, src + i);
-                if (P.has_V) {
-                    const char *pv = reinterpret_cast<const char *>(P.V + T->next_grid_off);
-                    for (int b = tid * 128; b < T->next_nq * 8; b += gsize * 128) prefetch_l2(pv + b);
+        for (int ip = 0; ip < npsi; ++ip) {
+            const double *x = psi + (long long)ip * nvec;
+            double *y = Hpsi + (long long)ip * nvec;
+            // gather (tabPackedBasis_TO_tabR_AT_iG); V of the term goes to the acc buffer, where the
+            // LAST pass reads and overwrites it element by element
+            if (nb0 == 1) {
+                // all mapping entries of this lane first, then all packed-psi / V loads: two memory latencies per term
+                int mreg[EVR_GS_MAX];
+#pragma unroll
+                for (int k = 0; k < EVR_GS_MAX; ++k) {
+                    const int j = tid + k * gsize;
+                    mreg[k] = (j < nq && !(P.dbg & 2)) ? __ldg(mp + j) : 0;
                 }
-                const char *pm = reinterpret_cast<const char *>(P.map + T->next2_map_off);
-                for (int b = tid * 128; b < T->next2_nq * 4; b += gsize * 128) prefetch_l2(pm + b);
+                double xv[EVR_GS_MAX];
+#pragma unroll
+                for (int k = 0; k < EVR_GS_MAX; ++k) xv[k] = (mreg[k] > 0) ? __ldg(x + (mreg[k] - 1)) : 0.0;
+                if (hasV && !(P.dbg & 8)) {
+                    double vv[EVR_GS_MAX];
+#pragma unroll
+                    for (int k = 0; k < EVR_GS_MAX; ++k) { const int j = tid + k * gsize; vv[k] = (j < nq) ? __ldg(Vt + j) : 0.0; }
+#pragma unroll
+                    for (int k = 0; k < EVR_GS_MAX; ++k) { const int j = tid + k * gsize; if (j < nq) s_acc[j] = vv[k]; }
+                }
+#pragma unroll
+                for (int k = 0; k < EVR_GS_MAX; ++k) { const int j = tid + k * gsize; if (j < nq) s_psi[j] = xv[k]; }
+            } else {
+                for (int j = tid; j < nq; j += gsize) {
+                    const int m = __ldg(mp + j);
+                    for (int c = 0; c < nb0; ++c)
+                        s_psi[c * nq + j] = (m > 0) ? __ldg(x + (long long)c * P.nb + (m - 1)) : 0.0;
+                }
             }
-            cp_async_commit();                                    // [V]
+            group_sync(gsize, group);
 
             PassArgs A;
             A.psi = s_psi; A.acc = s_acc; A.nq = nq; A.nb0 = nb0; A.vshift = T->vshift; A.tid = tid; A.nthr = gsize;
@@ -458,31 +443,15 @@ sg4_term_kernel_fast(const FastPlanDev P, const FastClassDev Cc, const int npsi,
                 const FastGroup &Gr = T->g[g];
                 A.stride = Gr.stride; A.magic = Gr.magic; A.m1 = Gr.mat1; A.m2 = Gr.mat2;
             };
-            int g_done = 0;
-            if (G >= 2) {   // first B -> G pass overlaps the landing of [M]   (BDP_TO_GDP_OF_SmolyakRep)
-                set_group(0);
-                dispatch_pass<PASS_B2G, MS, RT>(T->g[0].tmpl, T->g[0].n1, A);
-                g_done = 1;
-            }
-            // [M] (mapping slice of the next term) has landed -> issue the gather of the next item
-            cp_async_wait<1>();
-            group_sync(gsize, group);
-            if (!last_ip) issue_gather(ps ^ 1, ts, nq, psi + (long long)(ip + 1) * nvec);
-            else if (has_next_term) issue_gather(ps ^ 1, ts ^ 1, T->next_nq, psi);
-            cp_async_commit();                                    // [A]
             if (G == 0) {
-                cp_async_wait<1>();                               // [V]
-                group_sync(gsize, group);
                 if (tid < nb0) s_acc[tid] = (T->vshift + (hasV ? s_acc[tid] : 0.0)) * s_psi[tid];
                 group_sync(gsize, group);
             } else {
-                for (int g = g_done; g < G - 1; ++g) {            // remaining B -> G
+                for (int g = 0; g < G - 1; ++g) {                 // B -> G (BDP_TO_GDP_OF_SmolyakRep)
                     set_group(g);
                     dispatch_pass<PASS_B2G, MS, RT>(T->g[g].tmpl, T->g[g].n1, A);
                     group_sync(gsize, group);
                 }
-                cp_async_wait<1>();                               // [V] landed (and the next descriptor)
-                group_sync(gsize, group);
                 // last group: B -> G, (V+shift) psi, its kinetic part (, its G -> B when it is the only group)
                 set_group(G - 1);
                 A.hasV = hasV ? 1 : 0;
@@ -494,7 +463,6 @@ sg4_term_kernel_fast(const FastPlanDev P, const FastClassDev Cc, const int npsi,
             }
             if (!v_fused && P.has_V) {
                 // channel-coupling potential: acc(q,i) += sum_j V(q,i,j) psi(q,j)   (sub_OpPsi_SG4.f90:1521-1525)
-                const double *Vt = P.V + T->grid_off;
                 for (int q = tid; q < nq; q += gsize) {
                     double pj[EVR_MAXCH];
 #pragma unroll
@@ -527,24 +495,33 @@ sg4_term_kernel_fast(const FastPlanDev P, const FastClassDev Cc, const int npsi,
                     group_sync(gsize, group);
                 }
             }
-            // weighted scatter-add (tabR_AT_iG_TO_tabPackedBasis); the mapping slice is still in smem
+            // weighted scatter-add (tabR_AT_iG_TO_tabPackedBasis)
             {
                 const double weight = T->weight;
-                double *y = Hpsi + (long long)ip * nvec;
-                for (int j = tid; j < nq; j += gsize) {
-                    const int m = (P.dbg & 1) ? 0 : smap[j];
-                    if (m > 0)
-                        for (int c = 0; c < nb0; ++c)
-                            atomicAdd(y + (long long)c * P.nb + (m - 1), weight * s_acc[c * nq + j]);
+                if (nb0 == 1) {
+                    int mreg[EVR_GS_MAX];
+#pragma unroll
+                    for (int k = 0; k < EVR_GS_MAX; ++k) {
+                        const int j = tid + k * gsize;
+                        mreg[k] = (j < nq && !(P.dbg & 1)) ? __ldg(mp + j) : 0;
+                    }
+#pragma unroll
+                    for (int k = 0; k < EVR_GS_MAX; ++k) {
+                        const int j = tid + k * gsize;
+                        if (mreg[k] > 0) atomicAdd(y + (mreg[k] - 1), weight * s_acc[j]);
+                    }
+                } else {
+                    for (int j = tid; j < nq; j += gsize) {
+                        const int m = __ldg(mp + j);
+                        if (m > 0)
+                            for (int c = 0; c < nb0; ++c)
+                                atomicAdd(y + (long long)c * P.nb + (m - 1), weight * s_acc[c * nq + j]);
+                    }
                 }
             }
             group_sync(gsize, group);
-            // [M]: mapping slice of the term after next goes into the slot this term just released
-            if (last_ip && T->next2_nq > 0) issue_map(ts, T->next2_map_off, T->next2_nq);
-            cp_async_commit();                                    // [M]
         }
     }
-    cp_async_wait<0>();
 }
 
 } // namespace evr

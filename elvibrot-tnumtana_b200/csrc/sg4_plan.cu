@@ -434,36 +434,31 @@ static int build_fast_path(evr_sg4_plan *p, int nb_Term, const int32_t *term_mod
     }
     if (!ok) return 0;
     // launch configuration per size class + "next term" prefetch links
-    CUDA_TRY(cudaFuncSetAttribute(evr::sg4_term_kernel_fast<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    CUDA_TRY(cudaFuncSetAttribute(evr::sg4_term_kernel_fast<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    CUDA_TRY(cudaFuncSetAttribute(evr::sg4_term_kernel_fast<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    CUDA_TRY(cudaFuncSetAttribute(evr::sg4_term_kernel_fast<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CUDA_TRY(cudaFuncSetAttribute(evr::sg4_term_kernel_fast<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CUDA_TRY(cudaFuncSetAttribute(evr::sg4_term_kernel_fast<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CUDA_TRY(cudaFuncSetAttribute(evr::sg4_term_kernel_fast<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CUDA_TRY(cudaFuncSetAttribute(evr::sg4_term_kernel_fast<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     p->n_classes = 0;
     {
         int w0 = 0;
         for (int c = 0; c < 6; ++c) {
             int w1 = w0;
-            int64_t cap = 1, mapcap = 1;
-            while (w1 < p->n_terms && class_of(forder[w1]) == c) {
-                cap = std::max<int64_t>(cap, (int64_t)fterms[w1].nq * nb0);
-                mapcap = std::max<int64_t>(mapcap, (int64_t)fterms[w1].nq);
-                ++w1;
-            }
-            mapcap = (mapcap + 1) & ~(int64_t)1;      // keep the following buffers 8-byte aligned
+            int64_t cap = 1;
+            while (w1 < p->n_terms && class_of(forder[w1]) == c) { cap = std::max<int64_t>(cap, (int64_t)fterms[w1].nq * nb0); ++w1; }
             if (w1 == w0) continue;
-            const int gsize = class_gsize[c], ngrp = 128 / gsize;
-            const size_t per_group = (size_t)3 * cap * sizeof(double) + 2 * sizeof(evr::FastTermDev) + (size_t)2 * mapcap * sizeof(int32_t);
-            const size_t smem = per_group * ngrp + (pool_in_smem ? pool.size() * sizeof(double) : 0);
-            if (smem > 200 * 1024) return 0;
-            int occ = 0;
             const bool rt = (c >= 3);
-            if (pool_in_smem && !rt) CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, evr::sg4_term_kernel_fast<true, false>, 128, smem));
-            else if (!pool_in_smem && !rt) CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, evr::sg4_term_kernel_fast<false, false>, 128, smem));
-            else if (pool_in_smem) CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, evr::sg4_term_kernel_fast<true, true>, 128, smem));
-            else CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, evr::sg4_term_kernel_fast<false, true>, 128, smem));
-            if (occ < 1) return 0;
+            const int gsize = class_gsize[c];
+            const size_t per_group = (size_t)2 * cap * sizeof(double) + 2 * sizeof(evr::FastTermDev);
+            if (nb0 == 1 && (cap + gsize - 1) / gsize > EVR_GS_MAX) return 0;
+            const size_t pool_bytes = pool_in_smem ? pool.size() * sizeof(double) : 0;
+            const size_t budget = 227 * 1024;
+            if (pool_bytes + per_group > budget) return 0;
+            int ngrp = (int)std::min<size_t>((budget - pool_bytes) / per_group, (size_t)(EVR_FAST_MAX_THREADS / gsize));
+            if (gsize > 32) ngrp = std::min(ngrp, 15);          // named barriers 1..15
+            ngrp = std::max(1, std::min(ngrp, (w1 - w0 + p->sm_count - 1) / p->sm_count));
+            const size_t smem = pool_bytes + per_group * ngrp;
             const int n = w1 - w0;
-            const int ctas = std::max(1, std::min((n + ngrp - 1) / ngrp, p->sm_count * occ));
+            const int ctas = std::max(1, std::min((n + ngrp - 1) / ngrp, p->sm_count));
             const int step = ctas * ngrp;
             for (int w = w0; w < w1; ++w) {
                 evr::FastTermDev &F = fterms[w];
@@ -473,7 +468,7 @@ static int build_fast_path(evr_sg4_plan *p, int nb_Term, const int32_t *term_mod
                 else { F.next2_map_off = 0; F.next2_nq = 0; }
             }
             evr::FastClassDev &C = p->fclass[p->n_classes];
-            C.term_begin = w0; C.n_terms = n; C.gsize = gsize; C.rt = rt ? 1 : 0; C.cap = (int)cap; C.mapcap = (int)mapcap;
+            C.term_begin = w0; C.n_terms = n; C.gsize = gsize; C.rt = rt ? 1 : 0; C.cap = (int)cap; C.cta_threads = ngrp * gsize;
             p->fclass_smem[p->n_classes] = smem; p->fclass_ctas[p->n_classes] = ctas;
             ++p->n_classes;
             w0 = w1;
@@ -572,13 +567,13 @@ static int launch(evr_sg4_plan *p, int npsi, const double *d_psi, double *d_Hpsi
             for (int c = 0; c < p->n_classes; ++c) {
                 const bool ms = p->fast_pool_in_smem, rt = p->fclass[c].rt != 0;
                 if (ms && !rt)
-                    evr::sg4_term_kernel_fast<true, false><<<p->fclass_ctas[c], 128, p->fclass_smem[c], st>>>(p->fpd, p->fclass[c], npsi, d_psi, d_Hpsi);
+                    evr::sg4_term_kernel_fast<true, false><<<p->fclass_ctas[c], p->fclass[c].cta_threads, p->fclass_smem[c], st>>>(p->fpd, p->fclass[c], npsi, d_psi, d_Hpsi);
                 else if (!ms && !rt)
-                    evr::sg4_term_kernel_fast<false, false><<<p->fclass_ctas[c], 128, p->fclass_smem[c], st>>>(p->fpd, p->fclass[c], npsi, d_psi, d_Hpsi);
+                    evr::sg4_term_kernel_fast<false, false><<<p->fclass_ctas[c], p->fclass[c].cta_threads, p->fclass_smem[c], st>>>(p->fpd, p->fclass[c], npsi, d_psi, d_Hpsi);
                 else if (ms)
-                    evr::sg4_term_kernel_fast<true, true><<<p->fclass_ctas[c], 128, p->fclass_smem[c], st>>>(p->fpd, p->fclass[c], npsi, d_psi, d_Hpsi);
+                    evr::sg4_term_kernel_fast<true, true><<<p->fclass_ctas[c], p->fclass[c].cta_threads, p->fclass_smem[c], st>>>(p->fpd, p->fclass[c], npsi, d_psi, d_Hpsi);
                 else
-                    evr::sg4_term_kernel_fast<false, true><<<p->fclass_ctas[c], 128, p->fclass_smem[c], st>>>(p->fpd, p->fclass[c], npsi, d_psi, d_Hpsi);
+                    evr::sg4_term_kernel_fast<false, true><<<p->fclass_ctas[c], p->fclass[c].cta_threads, p->fclass_smem[c], st>>>(p->fpd, p->fclass[c], npsi, d_psi, d_Hpsi);
                 p->launches += 1;
             }
         } else {
