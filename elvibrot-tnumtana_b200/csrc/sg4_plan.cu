@@ -78,6 +78,8 @@ struct evr_sg4_plan {
     double *d_psi = nullptr, *d_Hpsi = nullptr;   // staging for the host-buffer entry point
     int64_t stage_cap = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t side[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // class kernels overlap their tails
+    cudaEvent_t ev_fork = nullptr, ev_join[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     size_t smem_bytes = 0;
     int grid_ctas = 0;
     evr::PlanDev pd{};
@@ -229,6 +231,13 @@ extern "C" int evr_sg4_plan_create(evr_sg4_plan **out, int device,
     if (rc) { evr_sg4_plan_destroy(&p); return 1; }
     if (cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking) != cudaSuccess) {
         evr_sg4_plan_destroy(&p); return fail("evr_sg4_plan_create: cudaStreamCreate failed");
+    }
+    if (!getenv("EVR_SG4_SINGLE_STREAM")) {
+        bool ok_ev = cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming) == cudaSuccess;
+        for (int c = 1; c < 6 && ok_ev; ++c)
+            ok_ev = cudaStreamCreateWithFlags(&p->side[c], cudaStreamNonBlocking) == cudaSuccess &&
+                    cudaEventCreateWithFlags(&p->ev_join[c], cudaEventDisableTiming) == cudaSuccess;
+        if (!ok_ev) { evr_sg4_plan_destroy(&p); return fail("evr_sg4_plan_create: side stream/event creation failed"); }
     }
 
     p->smem_bytes = (size_t)2 * p->cap * sizeof(double) + (size_t)(4 * nT + 5 * D) * sizeof(int);
@@ -564,7 +573,12 @@ static int launch(evr_sg4_plan *p, int npsi, const double *d_psi, double *d_Hpsi
     CUDA_TRY(cudaMemsetAsync(d_Hpsi, 0, bytes, st));                 // reference zeroes OpPsi (:765)
     if (p->n_terms > 0) {
         if (p->fast) {
+            const bool multi = p->n_classes > 1 && p->ev_fork != nullptr;
+            if (multi) CUDA_TRY(cudaEventRecord(p->ev_fork, st));
             for (int c = 0; c < p->n_classes; ++c) {
+                cudaStream_t st_main = st;
+                cudaStream_t st = (multi && c > 0) ? p->side[c] : st_main;
+                if (multi && c > 0) CUDA_TRY(cudaStreamWaitEvent(st, p->ev_fork, 0));
                 const bool ms = p->fast_pool_in_smem, rt = p->fclass[c].rt != 0;
                 if (ms && !rt)
                     evr::sg4_term_kernel_fast<true, false><<<p->fclass_ctas[c], p->fclass[c].cta_threads, p->fclass_smem[c], st>>>(p->fpd, p->fclass[c], npsi, d_psi, d_Hpsi);
@@ -575,6 +589,10 @@ static int launch(evr_sg4_plan *p, int npsi, const double *d_psi, double *d_Hpsi
                 else
                     evr::sg4_term_kernel_fast<false, true><<<p->fclass_ctas[c], p->fclass[c].cta_threads, p->fclass_smem[c], st>>>(p->fpd, p->fclass[c], npsi, d_psi, d_Hpsi);
                 p->launches += 1;
+                if (multi && c > 0) {
+                    CUDA_TRY(cudaEventRecord(p->ev_join[c], st));
+                    CUDA_TRY(cudaStreamWaitEvent(st_main, p->ev_join[c], 0));
+                }
             }
         } else {
             evr::sg4_term_kernel_generic<<<p->grid_ctas, 256, p->smem_bytes, st>>>(p->pd, npsi, d_psi, d_Hpsi);
@@ -648,6 +666,8 @@ extern "C" int evr_sg4_plan_destroy(evr_sg4_plan **pp)
     cudaFree(p->d_opterms); cudaFree(p->d_grids); cudaFree(p->d_psi); cudaFree(p->d_Hpsi);
     cudaFree(p->d_fterms); cudaFree(p->d_fmap); cudaFree(p->d_fmats); cudaFree(p->d_fV);
     if (p->stream) cudaStreamDestroy(p->stream);
+    for (int c = 0; c < 6; ++c) { if (p->side[c]) cudaStreamDestroy(p->side[c]); if (p->ev_join[c]) cudaEventDestroy(p->ev_join[c]); }
+    if (p->ev_fork) cudaEventDestroy(p->ev_fork);
     delete p;
     *pp = nullptr;
     return 0;

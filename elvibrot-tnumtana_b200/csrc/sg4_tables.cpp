@@ -240,3 +240,25 @@ extern "C" int evr_sg4_ini_iGs(int nb_SG, int np, int rank, int *iG_begin, int *
     *iG_begin = b; *iG_end = e;
     return 0;
 }
+
+// contiguous ranges with (nearly) equal cumulative cost: boundary r is the first term at which the
+// inclusive prefix sum reaches r/np of the total.
+extern "C" int evr_sg4_balanced_iGs(int nb_SG, const int32_t *cost, int np, int rank, int *iG_begin, int *iG_end)
+{
+    if (np < 1 || rank < 0 || rank >= np || nb_SG < 0 || !cost || !iG_begin || !iG_end)
+        return evr::fail("evr_sg4_balanced_iGs: bad arguments");
+    int64_t total = 0;
+    for (int i = 0; i < nb_SG; ++i) { if (cost[i] < 0) return evr::fail("evr_sg4_balanced_iGs: negative cost"); total += cost[i]; }
+    auto boundary = [&](int r) {
+        if (r <= 0) return 0;
+        if (r >= np) return nb_SG;
+        const double target = (double)total * r / np;
+        int64_t acc = 0;
+        for (int i = 0; i < nb_SG; ++i) { acc += cost[i]; if ((double)acc >= target) return i + 1; }
+        return nb_SG;
+    };
+    *iG_begin = boundary(rank);
+    *iG_end = boundary(rank + 1);
+    if (*iG_end < *iG_begin) *iG_end = *iG_begin;
+    return 0;
+}

@@ -23,7 +23,7 @@ INFO_SMEM_BYTES, INFO_GRID_CTAS, INFO_PATH, INFO_FLOPS_NPSI1 = 5, 6, 7, 8
 EXPORTS = [
     "evr_sg4_version", "evr_sg4_last_error",
     "evr_sg4_tables_build", "evr_sg4_tables_destroy", "evr_sg4_tables_size", "evr_sg4_tables_get",
-    "evr_sg4_ini_iGs",
+    "evr_sg4_ini_iGs", "evr_sg4_balanced_iGs",
     "evr_sg4_plan_create", "evr_sg4_plan_set_op", "evr_sg4_apply", "evr_sg4_apply_device",
     "evr_sg4_plan_info", "evr_sg4_plan_destroy",
 ]
@@ -68,6 +68,8 @@ def lib():
     L.evr_sg4_tables_get.argtypes = [vp, i32, vp]
     L.evr_sg4_ini_iGs.restype = i32
     L.evr_sg4_ini_iGs.argtypes = [i32, i32, i32, C.POINTER(i32), C.POINTER(i32)]
+    L.evr_sg4_balanced_iGs.restype = i32
+    L.evr_sg4_balanced_iGs.argtypes = [i32, vp, i32, i32, C.POINTER(i32), C.POINTER(i32)]
     L.evr_sg4_plan_create.restype = i32
     L.evr_sg4_plan_create.argtypes = [C.POINTER(vp), i32, i32, i32, i32, i64, i32] + [vp] * 11 + [i32, i32]
     L.evr_sg4_plan_set_op.restype = i32

@@ -72,6 +72,12 @@ int     evr_sg4_tables_get(const evr_sg4_tables *t, int what, void *dst); /* cop
  * sub_Basis_SG4/sub_module_basis_BtoG_GtoB_SG4_MPI.f90:639-669 (0-based, end exclusive). */
 int evr_sg4_ini_iGs(int nb_SG, int np, int rank, int *iG_begin, int *iG_end);
 
+/* Same contiguous decomposition but balanced by work instead of by term count: the ranges hold
+ * (nearly) equal sums of cost[iG] (e.g. tab_nq_OF_SRep), the way the reference balances its OpenMP
+ * thread ranges by grid points (Set_nDval_init_FOR_SG4 version 1, sub_module_param_SGType2.f90:538-650)
+ * and its MPI ranges by timing (auto_iGs_MPI, sub_OpPsi_SG4_MPI.f90:2689-2815). */
+int evr_sg4_balanced_iGs(int nb_SG, const int32_t *cost, int np, int rank, int *iG_begin, int *iG_end);
+
 /* ---------------------------------------------------------------------------
  * Plan = device-resident copy of everything sub_TabOpPsi_FOR_SGtype4 reads from
  * para_Op%BasisnD (param_SGType2, WeightSG, tab_basisPrimSG), for the terms

@@ -89,3 +89,17 @@ def test_ini_iGs_matches_reference_formula(evr):
             assert b.value == prev
             prev = e.value
         assert prev == nb_SG
+
+
+def test_balanced_iGs_partitions_by_cost(evr):
+    b = evr.workloads.hm_sg4_basis(12, 4, 4, 1, 2)
+    cost = b.tab_nq_OF_SRep
+    for np_ in (1, 2, 3, 8):
+        prev, loads = 0, []
+        for r in range(np_):
+            lo, hi = evr.distributed.balanced_iGs(cost, np_, r)
+            assert lo == prev and hi >= lo
+            loads.append(int(cost[lo:hi].sum()))
+            prev = hi
+        assert prev == b.nb_SG and sum(loads) == b.nqq
+        assert max(loads) - min(loads) <= 2 * int(cost.max())
