@@ -59,7 +59,7 @@ struct FastClassDev {       // one launch per size class: terms [term_begin, ter
 struct FastPlanDev {
     int nb0, n_terms, has_V;
     int pool_len;           // doubles in the (de-duplicated) matrix pool
-    int dbg;                // experiment switches (EVR_SG4_DEBUG): 1 no scatter, 2 no gather, 4 no passes, 8 no V load
+    int dbg;                // experiment switch (EVR_SG4_DEBUG): 4 = skip the transform passes
     long long nb, NQ_local;
     const FastTermDev *terms;
     const int32_t *map;     // permuted to the internal layout
@@ -189,7 +189,7 @@ __device__ __forceinline__ int tile_origin(const int t, const int stride, const 
     return t + stride * (tile - 1) * hi;           // lo + stride*tile*hi with lo = t - hi*stride
 }
 
-template <int N1, int N2, int KIND, bool MS>
+template <int N1, int N2, int KIND, bool MS, bool HV, bool FG, bool SP>
 __device__ __forceinline__ void run_pass(const PassArgs &A)
 {
     constexpr int NN1 = N1 * N1, NN2 = N2 * N2, TILE = N1 * N2;
@@ -213,9 +213,9 @@ __device__ __forceinline__ void run_pass(const PassArgs &A)
             } else if (KIND == PASS_LAST) {
                 tile_load<N1, N2>(v, psi + q0, stride);
                 tile_xform<N1, N2, MS>(v, B1, B2);
-                if (A.store_psi) tile_store<N1, N2>(v, psi + q0, stride);
+                if (SP) tile_store<N1, N2>(v, psi + q0, stride);
                 double a[N2][N1];
-                if (A.hasV) {
+                if (HV) {
                     tile_load<N1, N2>(a, acc + q0, stride);
 #pragma unroll
                     for (int j = 0; j < N2; ++j)
@@ -228,14 +228,14 @@ __device__ __forceinline__ void run_pass(const PassArgs &A)
                         for (int i = 0; i < N1; ++i) a[j][i] = A.vshift * v[j][i];
                 }
                 tile_keo<N1, N2, MS>(a, v, T1, T2);
-                if (A.fuse_g2b) tile_xform<N1, N2, MS>(a, W1, W2);
+                if (FG) tile_xform<N1, N2, MS>(a, W1, W2);
                 tile_store<N1, N2>(a, acc + q0, stride);
             } else {
                 double a[N2][N1];
                 tile_load<N1, N2>(v, psi + q0, stride);
                 tile_load<N1, N2>(a, acc + q0, stride);
                 tile_keo<N1, N2, MS>(a, v, T1, T2);
-                if (A.fuse_g2b) tile_xform<N1, N2, MS>(a, W1, W2);
+                if (FG) tile_xform<N1, N2, MS>(a, W1, W2);
                 tile_store<N1, N2>(a, acc + q0, stride);
             }
         }
@@ -304,14 +304,14 @@ __device__ __forceinline__ void run_pass_rt(const PassArgs &A, const int kind, c
 #define EVR_TMPL_LIST(X) X(1, 3, 1) X(2, 5, 1) X(3, 7, 1) X(4, 3, 3) X(7, 2, 1) X(8, 2, 3) X(9, 4, 1) X(10, 2, 2) \
     X(11, 9, 1) X(12, 11, 1) X(13, 13, 1) X(14, 15, 1) X(15, 6, 1) X(16, 8, 1)
 
-template <int KIND, bool MS, bool RT>
+template <int KIND, bool MS, bool RT, bool HV, bool FG, bool SP>
 __device__ __forceinline__ void dispatch_pass(const int tmpl, const int n1, const PassArgs &A)
 {
     if (RT) {                    // terms with a mode size that has no template: runtime-size single-mode tiles only
         run_pass_rt<MS>(A, KIND, n1);
     } else {
         switch (tmpl) {
-#define X(id, a, b) case id: run_pass<a, b, KIND, MS>(A); break;
+#define X(id, a, b) case id: run_pass<a, b, KIND, MS, HV, FG, SP>(A); break;
             EVR_TMPL_LIST(X)
 #undef X
         default: break;          // unreachable: the plan sends such terms to the RT instantiation
@@ -340,7 +340,7 @@ __device__ __forceinline__ void cp_async8(void *dst, const void *src)
 __device__ __forceinline__ void cp_async_commit_wait_all() { asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory"); }
 
 #define EVR_FAST_MAX_THREADS 768
-#define EVR_GS_MAX 18       // max elements per thread in gather/scatter: ceil(cap_class / gsize) <= 18 (plan checks)
+#define EVR_GB 6            // gather/scatter batch: independent loads in flight per lane
 
 template <bool MS, bool RT>
 __global__ void __launch_bounds__(EVR_FAST_MAX_THREADS, 1)
@@ -408,25 +408,29 @@ sg4_term_kernel_fast(const FastPlanDev P, const FastClassDev Cc, const int npsi,
             // gather (tabPackedBasis_TO_tabR_AT_iG); V of the term goes to the acc buffer, where the
             // LAST pass reads and overwrites it element by element
             if (nb0 == 1) {
-                // all mapping entries of this lane first, then all packed-psi / V loads: two memory latencies per term
-                int mreg[EVR_GS_MAX];
+                // batches of EVR_GB elements per lane: all mapping entries of the batch first, then the dependent
+                // packed-psi loads and the V loads (two memory latencies per batch)
+                const int niter = (nq + gsize - 1) / gsize;
+                for (int k0 = 0; k0 < niter; k0 += EVR_GB) {
+                    int mreg[EVR_GB];
 #pragma unroll
-                for (int k = 0; k < EVR_GS_MAX; ++k) {
-                    const int j = tid + k * gsize;
-                    mreg[k] = (j < nq && !(P.dbg & 2)) ? __ldg(mp + j) : 0;
+                    for (int u = 0; u < EVR_GB; ++u) {
+                        const int j = tid + (k0 + u) * gsize;
+                        mreg[u] = (j < nq) ? __ldg(mp + j) : 0;
+                    }
+                    double xv[EVR_GB], vv[EVR_GB];
+#pragma unroll
+                    for (int u = 0; u < EVR_GB; ++u) {
+                        const int j = tid + (k0 + u) * gsize;
+                        xv[u] = (mreg[u] > 0) ? __ldg(x + (mreg[u] - 1)) : 0.0;
+                        vv[u] = (hasV && j < nq) ? __ldg(Vt + j) : 0.0;
+                    }
+#pragma unroll
+                    for (int u = 0; u < EVR_GB; ++u) {
+                        const int j = tid + (k0 + u) * gsize;
+                        if (j < nq) { s_psi[j] = xv[u]; if (hasV) s_acc[j] = vv[u]; }
+                    }
                 }
-                double xv[EVR_GS_MAX];
-#pragma unroll
-                for (int k = 0; k < EVR_GS_MAX; ++k) xv[k] = (mreg[k] > 0) ? __ldg(x + (mreg[k] - 1)) : 0.0;
-                if (hasV && !(P.dbg & 8)) {
-                    double vv[EVR_GS_MAX];
-#pragma unroll
-                    for (int k = 0; k < EVR_GS_MAX; ++k) { const int j = tid + k * gsize; vv[k] = (j < nq) ? __ldg(Vt + j) : 0.0; }
-#pragma unroll
-                    for (int k = 0; k < EVR_GS_MAX; ++k) { const int j = tid + k * gsize; if (j < nq) s_acc[j] = vv[k]; }
-                }
-#pragma unroll
-                for (int k = 0; k < EVR_GS_MAX; ++k) { const int j = tid + k * gsize; if (j < nq) s_psi[j] = xv[k]; }
             } else {
                 for (int j = tid; j < nq; j += gsize) {
                     const int m = __ldg(mp + j);
@@ -449,7 +453,7 @@ sg4_term_kernel_fast(const FastPlanDev P, const FastClassDev Cc, const int npsi,
             } else {
                 for (int g = 0; g < G - 1; ++g) {                 // B -> G (BDP_TO_GDP_OF_SmolyakRep)
                     set_group(g);
-                    dispatch_pass<PASS_B2G, MS, RT>(T->g[g].tmpl, T->g[g].n1, A);
+                    dispatch_pass<PASS_B2G, MS, RT, false, false, false>(T->g[g].tmpl, T->g[g].n1, A);
                     group_sync(gsize, group);
                 }
                 // last group: B -> G, (V+shift) psi, its kinetic part (, its G -> B when it is the only group)
@@ -457,7 +461,18 @@ sg4_term_kernel_fast(const FastPlanDev P, const FastClassDev Cc, const int npsi,
                 A.hasV = hasV ? 1 : 0;
                 A.fuse_g2b = (G == 1 && v_fused) ? 1 : 0;
                 A.store_psi = (G > 1 || !v_fused) ? 1 : 0;
-                dispatch_pass<PASS_LAST, MS, RT>(T->g[G - 1].tmpl, T->g[G - 1].n1, A);
+                {
+                    const int tm = T->g[G - 1].tmpl, n1 = T->g[G - 1].n1;
+                    if (A.fuse_g2b) {            // single group, V fused: B->G, V, T, G->B in one pass
+                        if (A.hasV) dispatch_pass<PASS_LAST, MS, RT, true, true, false>(tm, n1, A);
+                        else dispatch_pass<PASS_LAST, MS, RT, false, true, false>(tm, n1, A);
+                    } else if (A.store_psi) {
+                        if (A.hasV) dispatch_pass<PASS_LAST, MS, RT, true, false, true>(tm, n1, A);
+                        else dispatch_pass<PASS_LAST, MS, RT, false, false, true>(tm, n1, A);
+                    } else {
+                        dispatch_pass<PASS_LAST, MS, RT, false, false, false>(tm, n1, A);
+                    }
+                }
                 A.hasV = 0; A.store_psi = 0;
                 group_sync(gsize, group);
             }
@@ -483,7 +498,8 @@ sg4_term_kernel_fast(const FastPlanDev P, const FastClassDev Cc, const int npsi,
                 for (int g = G - 2; g >= 0; --g) {
                     set_group(g);
                     A.fuse_g2b = (g == 0) ? 1 : 0;
-                    dispatch_pass<PASS_KEO, MS, RT>(T->g[g].tmpl, T->g[g].n1, A);
+                    if (g == 0) dispatch_pass<PASS_KEO, MS, RT, false, true, false>(T->g[g].tmpl, T->g[g].n1, A);
+                    else dispatch_pass<PASS_KEO, MS, RT, false, false, false>(T->g[g].tmpl, T->g[g].n1, A);
                     group_sync(gsize, group);
                 }
                 A.fuse_g2b = 0;
@@ -491,7 +507,7 @@ sg4_term_kernel_fast(const FastPlanDev P, const FastClassDev Cc, const int npsi,
                 const int g_first = (G == 1) ? (v_fused ? 1 : 0) : 1;
                 for (int g = g_first; g < G; ++g) {
                     set_group(g);
-                    dispatch_pass<PASS_G2B, MS, RT>(T->g[g].tmpl, T->g[g].n1, A);
+                    dispatch_pass<PASS_G2B, MS, RT, false, false, false>(T->g[g].tmpl, T->g[g].n1, A);
                     group_sync(gsize, group);
                 }
             }
@@ -499,16 +515,19 @@ sg4_term_kernel_fast(const FastPlanDev P, const FastClassDev Cc, const int npsi,
             {
                 const double weight = T->weight;
                 if (nb0 == 1) {
-                    int mreg[EVR_GS_MAX];
+                    const int niter = (nq + gsize - 1) / gsize;
+                    for (int k0 = 0; k0 < niter; k0 += EVR_GB) {
+                        int mreg[EVR_GB];
 #pragma unroll
-                    for (int k = 0; k < EVR_GS_MAX; ++k) {
-                        const int j = tid + k * gsize;
-                        mreg[k] = (j < nq && !(P.dbg & 1)) ? __ldg(mp + j) : 0;
-                    }
+                        for (int u = 0; u < EVR_GB; ++u) {
+                            const int j = tid + (k0 + u) * gsize;
+                            mreg[u] = (j < nq) ? __ldg(mp + j) : 0;
+                        }
 #pragma unroll
-                    for (int k = 0; k < EVR_GS_MAX; ++k) {
-                        const int j = tid + k * gsize;
-                        if (mreg[k] > 0) atomicAdd(y + (mreg[k] - 1), weight * s_acc[j]);
+                        for (int u = 0; u < EVR_GB; ++u) {
+                            const int j = tid + (k0 + u) * gsize;
+                            if (mreg[u] > 0) atomicAdd(y + (mreg[u] - 1), weight * s_acc[j]);
+                        }
                     }
                 } else {
                     for (int j = tid; j < nq; j += gsize) {

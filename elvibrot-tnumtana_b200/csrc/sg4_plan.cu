@@ -458,7 +458,6 @@ static int build_fast_path(evr_sg4_plan *p, int nb_Term, const int32_t *term_mod
             const bool rt = (c >= 3);
             const int gsize = class_gsize[c];
             const size_t per_group = (size_t)2 * cap * sizeof(double) + 2 * sizeof(evr::FastTermDev);
-            if (nb0 == 1 && (cap + gsize - 1) / gsize > EVR_GS_MAX) return 0;
             const size_t pool_bytes = pool_in_smem ? pool.size() * sizeof(double) : 0;
             const size_t budget = 227 * 1024;
             if (pool_bytes + per_group > budget) return 0;
