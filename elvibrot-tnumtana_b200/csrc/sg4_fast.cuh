@@ -62,7 +62,8 @@ struct FastPlanDev {
     int dbg;                // experiment switch (EVR_SG4_DEBUG): 4 = skip the transform passes
     long long nb, NQ_local;
     const FastTermDev *terms;
-    const int32_t *map;     // permuted to the internal layout
+    const int32_t *map;     // per term: internal packed index of each entry, sorted ascending (-1 = dropped)
+    const uint16_t *pos;    // per term: term-local position (internal layout) of each sorted entry
     const double *mats;     // pool of [B|BTw|T] blocks
     const double *V;        // [nb0*nb0][NQ_local] permuted to the internal layout
 };
@@ -394,12 +395,15 @@ sg4_term_kernel_fast(const FastPlanDev P, const FastClassDev Cc, const int npsi,
         if (T->next_nq > 0) {   // pull the next term's mapping / V slices and descriptor into L2
             const char *pm = reinterpret_cast<const char *>(P.map + T->next_map_off);
             for (int b = tid * 128; b < T->next_nq * 4; b += gsize * 128) prefetch_l2(pm + b);
+            const char *pq = reinterpret_cast<const char *>(P.pos + T->next_map_off);
+            for (int b = tid * 128; b < T->next_nq * 2; b += gsize * 128) prefetch_l2(pq + b);
             if (P.has_V) {
                 const char *pv = reinterpret_cast<const char *>(P.V + T->next_grid_off);
                 for (int b = tid * 128; b < T->next_nq * 8; b += gsize * 128) prefetch_l2(pv + b);
             }
         }
         const int32_t *mp = P.map + T->map_off;
+        const uint16_t *pp = P.pos + T->map_off;
         const double *Vt = P.has_V ? P.V + T->grid_off : nullptr;
 
         for (int ip = 0; ip < npsi; ++ip) {
@@ -412,30 +416,31 @@ sg4_term_kernel_fast(const FastPlanDev P, const FastClassDev Cc, const int npsi,
                 // packed-psi loads and the V loads (two memory latencies per batch)
                 const int niter = (nq + gsize - 1) / gsize;
                 for (int k0 = 0; k0 < niter; k0 += EVR_GB) {
-                    int mreg[EVR_GB];
+                    int mreg[EVR_GB], preg[EVR_GB];
 #pragma unroll
                     for (int u = 0; u < EVR_GB; ++u) {
                         const int j = tid + (k0 + u) * gsize;
-                        mreg[u] = (j < nq) ? __ldg(mp + j) : 0;
+                        mreg[u] = (j < nq) ? __ldg(mp + j) : -1;
+                        preg[u] = (j < nq) ? (int)__ldg(pp + j) : 0;
                     }
                     double xv[EVR_GB], vv[EVR_GB];
 #pragma unroll
                     for (int u = 0; u < EVR_GB; ++u) {
                         const int j = tid + (k0 + u) * gsize;
-                        xv[u] = (mreg[u] > 0) ? __ldg(x + (mreg[u] - 1)) : 0.0;
+                        xv[u] = (mreg[u] >= 0) ? __ldg(x + mreg[u]) : 0.0;
                         vv[u] = (hasV && j < nq) ? __ldg(Vt + j) : 0.0;
                     }
 #pragma unroll
                     for (int u = 0; u < EVR_GB; ++u) {
                         const int j = tid + (k0 + u) * gsize;
-                        if (j < nq) { s_psi[j] = xv[u]; if (hasV) s_acc[j] = vv[u]; }
+                        if (j < nq) { s_psi[preg[u]] = xv[u]; if (hasV) s_acc[j] = vv[u]; }
                     }
                 }
             } else {
                 for (int j = tid; j < nq; j += gsize) {
-                    const int m = __ldg(mp + j);
+                    const int m = __ldg(mp + j), q = __ldg(pp + j);
                     for (int c = 0; c < nb0; ++c)
-                        s_psi[c * nq + j] = (m > 0) ? __ldg(x + (long long)c * P.nb + (m - 1)) : 0.0;
+                        s_psi[c * nq + q] = (m >= 0) ? __ldg(x + (long long)c * P.nb + m) : 0.0;
                 }
             }
             group_sync(gsize, group);
@@ -517,29 +522,46 @@ sg4_term_kernel_fast(const FastPlanDev P, const FastClassDev Cc, const int npsi,
                 if (nb0 == 1) {
                     const int niter = (nq + gsize - 1) / gsize;
                     for (int k0 = 0; k0 < niter; k0 += EVR_GB) {
-                        int mreg[EVR_GB];
+                        int mreg[EVR_GB], preg[EVR_GB];
 #pragma unroll
                         for (int u = 0; u < EVR_GB; ++u) {
                             const int j = tid + (k0 + u) * gsize;
-                            mreg[u] = (j < nq) ? __ldg(mp + j) : 0;
+                            mreg[u] = (j < nq) ? __ldg(mp + j) : -1;
+                            preg[u] = (j < nq) ? (int)__ldg(pp + j) : 0;
                         }
 #pragma unroll
-                        for (int u = 0; u < EVR_GB; ++u) {
-                            const int j = tid + (k0 + u) * gsize;
-                            if (mreg[u] > 0) atomicAdd(y + (mreg[u] - 1), weight * s_acc[j]);
-                        }
+                        for (int u = 0; u < EVR_GB; ++u)
+                            if (mreg[u] >= 0) atomicAdd(y + mreg[u], weight * s_acc[preg[u]]);
                     }
                 } else {
                     for (int j = tid; j < nq; j += gsize) {
-                        const int m = __ldg(mp + j);
-                        if (m > 0)
+                        const int m = __ldg(mp + j), q = __ldg(pp + j);
+                        if (m >= 0)
                             for (int c = 0; c < nb0; ++c)
-                                atomicAdd(y + (long long)c * P.nb + (m - 1), weight * s_acc[c * nq + j]);
+                                atomicAdd(y + (long long)c * P.nb + m, weight * s_acc[c * nq + q]);
                     }
                 }
             }
             group_sync(gsize, group);
         }
+    }
+}
+
+// packed vectors between the caller's order (RvecB) and the internal block order
+__global__ void sg4_permute_in(const int32_t *__restrict__ perm, const long long nb, const int nvecs,
+                               const double *__restrict__ src, double *__restrict__ dst)
+{
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nb; i += (long long)gridDim.x * blockDim.x) {
+        const int r = __ldg(perm + i);
+        for (int v = 0; v < nvecs; ++v) dst[v * nb + i] = __ldg(src + v * nb + r);
+    }
+}
+__global__ void sg4_permute_out(const int32_t *__restrict__ perm, const long long nb, const int nvecs,
+                                const double *__restrict__ src, double *__restrict__ dst)
+{
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nb; i += (long long)gridDim.x * blockDim.x) {
+        const int r = __ldg(perm + i);
+        for (int v = 0; v < nvecs; ++v) dst[v * nb + r] = src[v * nb + i];
     }
 }
 

@@ -15,6 +15,7 @@
 #include <cstdio>
 #include <cstring>
 #include <cstdlib>
+#include <climits>
 #include <map>
 #include <numeric>
 #include <string>
@@ -59,12 +60,17 @@ struct evr_sg4_plan {
     // fast path (sg4_fast.cuh)
     bool fast = false;
     evr::FastTermDev *d_fterms = nullptr;
-    int32_t *d_fmap = nullptr;
+    int32_t *d_fmap = nullptr;           // per term: internal packed index (sorted ascending), -1 = dropped
+    uint16_t *d_fpos = nullptr;          // per term: term-local position of each sorted entry
+    int32_t *d_perm = nullptr;           // internal packed order -> reference packed index (0-based)
+    double *d_psi_int = nullptr, *d_Hpsi_int = nullptr;   // packed vectors in the internal (block) order
+    int64_t int_cap = 0;
     double *d_fmats = nullptr, *d_fV = nullptr;
     evr::FastPlanDev fpd{};
     std::vector<double> h_cost;             // per local term
     int n_classes = 0;
     bool fast_pool_in_smem = false;
+    bool fast_block_order = false;
     evr::FastClassDev fclass[6];
     size_t fclass_smem[6] = {0, 0, 0, 0, 0, 0};
     int fclass_ctas[6] = {0, 0, 0, 0, 0, 0};
@@ -358,8 +364,35 @@ static int build_fast_path(evr_sg4_plan *p, int nb_Term, const int32_t *term_mod
         if (ca != cb) return ca < cb;
         return p->h_cost[a] > p->h_cost[b];
     });
+    // ---- internal order of the packed vector: functions reached by exactly the same set of Smolyak terms
+    // (= same level vector) are stored contiguously, so that every term reads/updates whole blocks and the
+    // gather/scatter of a warp touches a few contiguous runs instead of 32 separate sectors.
+    // The membership signature is a sum of per-term 64-bit hashes; no multi-index table is needed.
+    // The two permutation kernels cost ~12 us per H|psi>, so small problems keep the caller's order (identity
+    // permutation, term entries still sorted by address); EVR_SG4_BLOCK_ORDER=0/1 overrides the size heuristic.
+    std::vector<int32_t> inv_perm((size_t)p->nb), perm((size_t)p->nb);
+    bool block_order = p->NQ_local >= 8000000;
+    if (getenv("EVR_SG4_BLOCK_ORDER")) block_order = atoi(getenv("EVR_SG4_BLOCK_ORDER")) != 0;
+    p->fast_block_order = block_order;
+    if (!block_order) {
+        std::iota(perm.begin(), perm.end(), 0);
+        std::iota(inv_perm.begin(), inv_perm.end(), 0);
+    } else {
+        std::vector<uint64_t> sig((size_t)p->nb, 0);
+        for (int t = 0; t < p->n_terms; ++t) {
+            uint64_t h = (uint64_t)(p->iG_begin + t + 1) * 0x9E3779B97F4A7C15ull;
+            h ^= h >> 29; h *= 0xBF58476D1CE4E5B9ull; h ^= h >> 32;
+            const int32_t *m = p->h_map.data() + p->h_map_off[t];
+            const int n = p->h_tab_nb[p->iG_begin + t];
+            for (int j = 0; j < n; ++j) if (m[j] > 0) sig[m[j] - 1] += h;
+        }
+        std::iota(perm.begin(), perm.end(), 0);
+        std::stable_sort(perm.begin(), perm.end(), [&](int32_t a, int32_t b) { return sig[a] < sig[b]; });
+        for (int64_t i = 0; i < p->nb; ++i) inv_perm[perm[i]] = (int32_t)i;
+    }
     std::vector<evr::FastTermDev> fterms(p->n_terms);
     std::vector<int32_t> fmap((size_t)std::max<int64_t>(p->S_local, 1));
+    std::vector<uint16_t> fpos((size_t)std::max<int64_t>(p->S_local, 1));
     std::vector<double> fV;
     if (Vgrid) fV.resize((size_t)nb0 * nb0 * std::max<int64_t>(p->NQ_local, 1));
     bool ok = true;
@@ -428,17 +461,26 @@ static int build_fast_path(evr_sg4_plan *p, int nb_Term, const int32_t *term_mod
         int64_t q = 0;
         const int32_t *msrc = p->h_map.data() + F.map_off;
         int32_t *mdst = fmap.data() + F.map_off;
+        uint16_t *pdst = fpos.data() + F.map_off;
+        if (F.nq > 65535) { ok = false; continue; }
+        std::vector<std::pair<int32_t, uint16_t>> ent((size_t)F.nq);
         for (int qp = 0; qp < F.nq; ++qp) {
-            mdst[qp] = msrc[q];
+            const int32_t m = msrc[q];
+            ent[qp] = { m > 0 ? inv_perm[m - 1] : INT32_MAX, (uint16_t)qp };
             if (Vgrid)
                 for (int ij = 0; ij < nb0 * nb0; ++ij)
                     fV[(size_t)ij * p->NQ_local + F.grid_off + qp] = Vgrid[(size_t)ij * p->NQ_total + p->grid_start + F.grid_off + q];
-            for (int m = 0; m < nm; ++m) {
-                q += in_ref[m];
-                if (++idx[m] < in_n[m]) break;
-                q -= (int64_t)in_ref[m] * in_n[m];
-                idx[m] = 0;
+            for (int m2 = 0; m2 < nm; ++m2) {
+                q += in_ref[m2];
+                if (++idx[m2] < in_n[m2]) break;
+                q -= (int64_t)in_ref[m2] * in_n[m2];
+                idx[m2] = 0;
             }
+        }
+        std::sort(ent.begin(), ent.end());
+        for (int j = 0; j < F.nq; ++j) {
+            mdst[j] = (ent[j].first == INT32_MAX) ? -1 : ent[j].first;
+            pdst[j] = ent[j].second;
         }
     }
     if (!ok) return 0;
@@ -486,6 +528,9 @@ static int build_fast_path(evr_sg4_plan *p, int nb_Term, const int32_t *term_mod
     p->d_fterms = nullptr; p->d_fmap = nullptr; p->d_fmats = nullptr; p->d_fV = nullptr;
     if (upload(&p->d_fterms, fterms.data(), fterms.size())) return 1;
     if (upload(&p->d_fmap, fmap.data(), fmap.size())) return 1;
+    cudaFree(p->d_fpos); p->d_fpos = nullptr; cudaFree(p->d_perm); p->d_perm = nullptr;
+    if (upload(&p->d_fpos, fpos.data(), fpos.size())) return 1;
+    if (upload(&p->d_perm, perm.data(), perm.size())) return 1;
     if (upload(&p->d_fmats, pool.data(), pool.size())) return 1;
     if (Vgrid && upload(&p->d_fV, fV.data(), fV.size())) return 1;
     evr::FastPlanDev &f = p->fpd;
@@ -493,7 +538,7 @@ static int build_fast_path(evr_sg4_plan *p, int nb_Term, const int32_t *term_mod
     p->fast_pool_in_smem = pool_in_smem;
     f.dbg = getenv("EVR_SG4_DEBUG") ? atoi(getenv("EVR_SG4_DEBUG")) : 0;
     f.nb = p->nb; f.NQ_local = p->NQ_local;
-    f.terms = p->d_fterms; f.map = p->d_fmap; f.mats = p->d_fmats; f.V = p->d_fV;
+    f.terms = p->d_fterms; f.map = p->d_fmap; f.pos = p->d_fpos; f.mats = p->d_fmats; f.V = p->d_fV;
     p->fast = true;
     return 0;
 }
@@ -566,9 +611,27 @@ extern "C" int evr_sg4_plan_set_op(evr_sg4_plan *p, int type_Op, int nb_Term, co
     return 0;
 }
 
-static int launch(evr_sg4_plan *p, int npsi, const double *d_psi, double *d_Hpsi, cudaStream_t st)
+static int launch(evr_sg4_plan *p, int npsi, const double *d_psi_user, double *d_Hpsi_user, cudaStream_t st)
 {
     const size_t bytes = (size_t)npsi * p->nb * p->nb0 * sizeof(double);
+    const double *d_psi = d_psi_user;
+    double *d_Hpsi = d_Hpsi_user;
+    const bool use_int = p->fast && p->fast_block_order && p->n_terms > 0;
+    if (use_int) {
+        // fast path works on the packed vectors in the internal (block) order
+        const int64_t nvecs = (int64_t)npsi * p->nb0;
+        if (nvecs * p->nb > p->int_cap) {
+            cudaFree(p->d_psi_int); cudaFree(p->d_Hpsi_int); p->d_psi_int = p->d_Hpsi_int = nullptr; p->int_cap = 0;
+            CUDA_TRY(cudaMalloc((void **)&p->d_psi_int, bytes));
+            CUDA_TRY(cudaMalloc((void **)&p->d_Hpsi_int, bytes));
+            p->int_cap = nvecs * p->nb;
+        }
+        const int thr = 256;
+        const int blocks = (int)std::min<int64_t>((p->nb + thr - 1) / thr, 148 * 16);
+        evr::sg4_permute_in<<<blocks, thr, 0, st>>>(p->d_perm, p->nb, (int)nvecs, d_psi_user, p->d_psi_int);
+        p->launches += 1;
+        d_psi = p->d_psi_int; d_Hpsi = p->d_Hpsi_int;
+    }
     CUDA_TRY(cudaMemsetAsync(d_Hpsi, 0, bytes, st));                 // reference zeroes OpPsi (:765)
     if (p->n_terms > 0) {
         if (p->fast) {
@@ -597,6 +660,14 @@ static int launch(evr_sg4_plan *p, int npsi, const double *d_psi, double *d_Hpsi
             evr::sg4_term_kernel_generic<<<p->grid_ctas, 256, p->smem_bytes, st>>>(p->pd, npsi, d_psi, d_Hpsi);
             p->launches += 1;
         }
+        CUDA_TRY(cudaGetLastError());
+    }
+    if (use_int) {
+        const int64_t nvecs = (int64_t)npsi * p->nb0;
+        const int thr = 256;
+        const int blocks = (int)std::min<int64_t>((p->nb + thr - 1) / thr, 148 * 16);
+        evr::sg4_permute_out<<<blocks, thr, 0, st>>>(p->d_perm, p->nb, (int)nvecs, p->d_Hpsi_int, d_Hpsi_user);
+        p->launches += 1;
         CUDA_TRY(cudaGetLastError());
     }
     return 0;
@@ -664,6 +735,7 @@ extern "C" int evr_sg4_plan_destroy(evr_sg4_plan **pp)
     cudaFree(p->d_offB); cudaFree(p->d_offG); cudaFree(p->d_B); cudaFree(p->d_BTw); cudaFree(p->d_D1); cudaFree(p->d_D2);
     cudaFree(p->d_opterms); cudaFree(p->d_grids); cudaFree(p->d_psi); cudaFree(p->d_Hpsi);
     cudaFree(p->d_fterms); cudaFree(p->d_fmap); cudaFree(p->d_fmats); cudaFree(p->d_fV);
+    cudaFree(p->d_fpos); cudaFree(p->d_perm); cudaFree(p->d_psi_int); cudaFree(p->d_Hpsi_int);
     if (p->stream) cudaStreamDestroy(p->stream);
     for (int c = 0; c < 6; ++c) { if (p->side[c]) cudaStreamDestroy(p->side[c]); if (p->ev_join[c]) cudaEventDestroy(p->ev_join[c]); }
     if (p->ev_fork) cudaEventDestroy(p->ev_fork);
