@@ -33,8 +33,8 @@ struct FastGroup {
     unsigned magic;         // floor(2^32/stride)+1 : exact t/stride by __umulhi for t*stride < 2^32 (stride > 1)
     unsigned short n1, n2;  // n2 = 0: single mode
     unsigned short tmpl;    // template id (0 = runtime single)
-    unsigned short pad;
-    int mat1, mat2;         // offsets (doubles) of the [B|BTw|T] blocks of mode 1 / 2 in the matrix pool
+    unsigned short n3;      // > 0: three-mode cube tile (n1 = n2 = n3)
+    int mat1, mat2, mat3;   // offsets (doubles) of the [B|BTw|T] blocks of the modes in the matrix pool
 };
 
 struct FastTermDev {
@@ -52,6 +52,7 @@ struct FastClassDev {       // one launch per size class: terms [term_begin, ter
     int term_begin, n_terms;
     int gsize;              // threads cooperating on one term: 32, 64 or 128
     int rt;                 // 1: runtime-size tiles (RT instantiation of the kernel)
+    int tri;                // 1: terms with three-mode cube tiles (TRI instantiation, 512 threads)
     int cap;                // doubles per psi/acc buffer (max nq*nb0 of the class)
     int cta_threads;        // threads per CTA = groups per CTA * gsize (<= 768)
 };
@@ -89,10 +90,63 @@ __device__ __forceinline__ void tile_store(const double (&v)[N2][N1], double *bu
 #pragma unroll
         for (int i = 0; i < N1; ++i) buf[stride * (i + N1 * j)] = v[j][i];
 }
+// v <- (M (x) M) v for a square tile whose two modes share one matrix (e.g. equal Hm modes): every matrix
+// row is loaded once and used for both mode products
+template <int N, bool MS>
+__device__ __forceinline__ void tile_xform_same(double (&v)[N][N], const double *M)
+{
+    double m[N][N];
+#pragma unroll
+    for (int q = 0; q < N; ++q)
+#pragma unroll
+        for (int b = 0; b < N; ++b) m[q][b] = ldm<MS>(M, q + N * b);
+    double t[N][N];
+#pragma unroll
+    for (int j = 0; j < N; ++j)
+#pragma unroll
+        for (int q = 0; q < N; ++q) {
+            double s = m[q][0] * v[j][0];
+#pragma unroll
+            for (int b = 1; b < N; ++b) s = fma(m[q][b], v[j][b], s);
+            t[j][q] = s;
+        }
+#pragma unroll
+    for (int q = 0; q < N; ++q)
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            double s = m[q][0] * t[0][i];
+#pragma unroll
+            for (int b = 1; b < N; ++b) s = fma(m[q][b], t[b][i], s);
+            v[q][i] = s;
+        }
+}
+template <int N, bool MS>
+__device__ __forceinline__ void tile_keo_same(double (&a)[N][N], const double (&v)[N][N], const double *T)
+{
+    double m[N][N];
+#pragma unroll
+    for (int q = 0; q < N; ++q)
+#pragma unroll
+        for (int b = 0; b < N; ++b) m[q][b] = ldm<MS>(T, q + N * b);
+#pragma unroll
+    for (int j = 0; j < N; ++j)
+#pragma unroll
+        for (int q = 0; q < N; ++q) {
+            double s = a[j][q];
+#pragma unroll
+            for (int b = 0; b < N; ++b) s = fma(m[q][b], v[j][b], s);
+#pragma unroll
+            for (int b = 0; b < N; ++b) s = fma(m[j][b], v[b][q], s);
+            a[j][q] = s;
+        }
+}
 // v <- (M2 (x) M1) v        (one matrix ROW is held in registers at a time)
 template <int N1, int N2, bool MS>
 __device__ __forceinline__ void tile_xform(double (&v)[N2][N1], const double *M1, const double *M2)
 {
+    if constexpr (N1 == N2 && N1 <= 3) {
+        if (M1 == M2) { tile_xform_same<N1, MS>(v, M1); return; }
+    }
     {
         double t[N2][N1];
 #pragma unroll
@@ -138,6 +192,9 @@ __device__ __forceinline__ void tile_xform(double (&v)[N2][N1], const double *M1
 template <int N1, int N2, bool MS>
 __device__ __forceinline__ void tile_keo(double (&a)[N2][N1], const double (&v)[N2][N1], const double *T1, const double *T2)
 {
+    if constexpr (N1 == N2 && N1 <= 3) {
+        if (T1 == T2) { tile_keo_same<N1, MS>(a, v, T1); return; }
+    }
 #pragma unroll
     for (int q = 0; q < N1; ++q) {
         double mq[N1];
@@ -173,7 +230,7 @@ enum { PASS_B2G = 0, PASS_G2B = 1, PASS_LAST = 2, PASS_KEO = 3 };
 struct PassArgs {
     double *psi, *acc;          // shared-memory buffers of this item
     const double *pool;         // matrix pool (shared memory when MS, else global)
-    int m1, m2;                 // offsets of the [B|BTw|T] blocks of the two modes in the pool
+    int m1, m2, m3;             // offsets of the [B|BTw|T] blocks of the modes in the pool
     double vshift;
     int nq, nb0, stride;
     unsigned magic;
@@ -243,6 +300,150 @@ __device__ __forceinline__ void run_pass(const PassArgs &A)
     }
 }
 
+// ---- three-mode cube tiles (N x N x N values per thread, v[k][j][i], strides s, s*N, s*N*N) ----------
+template <int N, bool MS>
+__device__ __forceinline__ void load_mat(double (&m)[N][N], const double *M)
+{
+#pragma unroll
+    for (int q = 0; q < N; ++q)
+#pragma unroll
+        for (int b = 0; b < N; ++b) m[q][b] = ldm<MS>(M, q + N * b);
+}
+template <int N>
+__device__ __forceinline__ void cube_apply0(double (&v)[N][N][N], const double (&m)[N][N])
+{
+#pragma unroll
+    for (int k = 0; k < N; ++k)
+#pragma unroll
+        for (int j = 0; j < N; ++j) {
+            double t[N];
+#pragma unroll
+            for (int q = 0; q < N; ++q) {
+                double s = m[q][0] * v[k][j][0];
+#pragma unroll
+                for (int b = 1; b < N; ++b) s = fma(m[q][b], v[k][j][b], s);
+                t[q] = s;
+            }
+#pragma unroll
+            for (int q = 0; q < N; ++q) v[k][j][q] = t[q];
+        }
+}
+template <int N>
+__device__ __forceinline__ void cube_apply1(double (&v)[N][N][N], const double (&m)[N][N])
+{
+#pragma unroll
+    for (int k = 0; k < N; ++k)
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            double t[N];
+#pragma unroll
+            for (int q = 0; q < N; ++q) {
+                double s = m[q][0] * v[k][0][i];
+#pragma unroll
+                for (int b = 1; b < N; ++b) s = fma(m[q][b], v[k][b][i], s);
+                t[q] = s;
+            }
+#pragma unroll
+            for (int q = 0; q < N; ++q) v[k][q][i] = t[q];
+        }
+}
+template <int N>
+__device__ __forceinline__ void cube_apply2(double (&v)[N][N][N], const double (&m)[N][N])
+{
+#pragma unroll
+    for (int j = 0; j < N; ++j)
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            double t[N];
+#pragma unroll
+            for (int q = 0; q < N; ++q) {
+                double s = m[q][0] * v[0][j][i];
+#pragma unroll
+                for (int b = 1; b < N; ++b) s = fma(m[q][b], v[b][j][i], s);
+                t[q] = s;
+            }
+#pragma unroll
+            for (int q = 0; q < N; ++q) v[q][j][i] = t[q];
+        }
+}
+template <int N, bool MS>
+__device__ __forceinline__ void cube_xform(double (&v)[N][N][N], const double *M1, const double *M2, const double *M3)
+{
+    double m[N][N];
+    load_mat<N, MS>(m, M1);
+    cube_apply0<N>(v, m);
+    if (M2 != M1) load_mat<N, MS>(m, M2);
+    cube_apply1<N>(v, m);
+    if (M3 != M2) load_mat<N, MS>(m, M3);
+    cube_apply2<N>(v, m);
+}
+
+// cube passes: B2G / G2B in place; LAST and KEO write acc row by row (no second register tile)
+template <int N, int KIND, bool MS, bool HV, bool SP>
+__device__ __forceinline__ void run_pass_cube(const PassArgs &A)
+{
+    constexpr int NN = N * N, TILE = N * N * N;
+    const int ntiles = A.nq / TILE;
+    const double *B1 = A.pool + A.m1, *B2 = A.pool + A.m2, *B3 = A.pool + A.m3;
+    const int s1 = A.stride, s2 = A.stride * N, s3 = A.stride * NN;
+    for (int c = 0; c < A.nb0; ++c) {
+        double *psi = A.psi + c * A.nq, *acc = A.acc + c * A.nq;
+        for (int t = A.tid; t < ntiles; t += A.nthr) {
+            const int q0 = tile_origin(t, A.stride, A.magic, TILE);
+            double v[N][N][N];
+            double *src = (KIND == PASS_G2B) ? acc + q0 : psi + q0;
+#pragma unroll
+            for (int k = 0; k < N; ++k)
+#pragma unroll
+                for (int j = 0; j < N; ++j)
+#pragma unroll
+                    for (int i = 0; i < N; ++i) v[k][j][i] = src[s1 * i + s2 * j + s3 * k];
+            if (KIND == PASS_B2G || KIND == PASS_LAST) cube_xform<N, MS>(v, B1, B2, B3);
+            if (KIND == PASS_G2B) cube_xform<N, MS>(v, B1 + NN, B2 + NN, B3 + NN);
+            if (KIND == PASS_B2G || KIND == PASS_G2B || (KIND == PASS_LAST && SP)) {
+#pragma unroll
+                for (int k = 0; k < N; ++k)
+#pragma unroll
+                    for (int j = 0; j < N; ++j)
+#pragma unroll
+                        for (int i = 0; i < N; ++i) src[s1 * i + s2 * j + s3 * k] = v[k][j][i];
+            }
+            if (KIND == PASS_LAST || KIND == PASS_KEO) {
+                const double *T1 = B1 + 2 * NN, *T2 = B2 + 2 * NN, *T3 = B3 + 2 * NN;
+                double m1[N][N];
+                load_mat<N, MS>(m1, T1);
+                const bool same = (T2 == T1) && (T3 == T1);
+#pragma unroll
+                for (int k = 0; k < N; ++k) {
+                    double r3[N];
+#pragma unroll
+                    for (int b = 0; b < N; ++b) r3[b] = same ? m1[k][b] : ldm<MS>(T3, k + N * b);
+#pragma unroll
+                    for (int j = 0; j < N; ++j) {
+                        double r2[N];
+#pragma unroll
+                        for (int b = 0; b < N; ++b) r2[b] = same ? m1[j][b] : ldm<MS>(T2, j + N * b);
+                        double *arow = acc + q0 + s2 * j + s3 * k;
+#pragma unroll
+                        for (int i = 0; i < N; ++i) {
+                            double sacc;
+                            if (KIND == PASS_LAST) sacc = ((HV ? arow[s1 * i] : 0.0) + A.vshift) * v[k][j][i];
+                            else sacc = arow[s1 * i];
+#pragma unroll
+                            for (int b = 0; b < N; ++b) sacc = fma(m1[i][b], v[k][j][b], sacc);
+#pragma unroll
+                            for (int b = 0; b < N; ++b) sacc = fma(r2[b], v[k][b][i], sacc);
+#pragma unroll
+                            for (int b = 0; b < N; ++b) sacc = fma(r3[b], v[b][j][i], sacc);
+                            arow[s1 * i] = sacc;
+                        }
+                    }
+                }
+            }
+        }
+    }
+}
+
 // runtime-size single mode (n <= EVR_RT_NMAX): same passes with guarded, unrolled register arrays
 template <bool MS>
 __device__ __forceinline__ void run_pass_rt(const PassArgs &A, const int kind, const int n)
@@ -305,7 +506,10 @@ __device__ __forceinline__ void run_pass_rt(const PassArgs &A, const int kind, c
 #define EVR_TMPL_LIST(X) X(1, 3, 1) X(2, 5, 1) X(3, 7, 1) X(4, 3, 3) X(7, 2, 1) X(8, 2, 3) X(9, 4, 1) X(10, 2, 2) \
     X(11, 9, 1) X(12, 11, 1) X(13, 13, 1) X(14, 15, 1) X(15, 6, 1) X(16, 8, 1)
 
-template <int KIND, bool MS, bool RT, bool HV, bool FG, bool SP>
+#define EVR_TMPL_CUBE3 30    // template id of the 3x3x3 cube tile (only in the TRI instantiation of the kernel)
+#define EVR_TMPL_CUBE2 31    // 2x2x2
+
+template <int KIND, bool MS, bool RT, bool TRI, bool HV, bool FG, bool SP>
 __device__ __forceinline__ void dispatch_pass(const int tmpl, const int n1, const PassArgs &A)
 {
     if (RT) {                    // terms with a mode size that has no template: runtime-size single-mode tiles only
@@ -315,6 +519,8 @@ __device__ __forceinline__ void dispatch_pass(const int tmpl, const int n1, cons
 #define X(id, a, b) case id: run_pass<a, b, KIND, MS, HV, FG, SP>(A); break;
             EVR_TMPL_LIST(X)
 #undef X
+        case EVR_TMPL_CUBE3: if (TRI) run_pass_cube<3, KIND, MS, HV, SP>(A); break;
+        case EVR_TMPL_CUBE2: if (TRI) run_pass_cube<2, KIND, MS, HV, SP>(A); break;
         default: break;          // unreachable: the plan sends such terms to the RT instantiation
         }
     }
@@ -341,10 +547,11 @@ __device__ __forceinline__ void cp_async8(void *dst, const void *src)
 __device__ __forceinline__ void cp_async_commit_wait_all() { asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory"); }
 
 #define EVR_FAST_MAX_THREADS 768
+#define EVR_FAST_MAX_THREADS_TRI 512   // cube tiles keep 27 values + a 3x3 matrix in registers: 128 registers per thread
 #define EVR_GB 6            // gather/scatter batch: independent loads in flight per lane
 
-template <bool MS, bool RT>
-__global__ void __launch_bounds__(EVR_FAST_MAX_THREADS, 1)
+template <bool MS, bool RT, bool TRI>
+__global__ void __launch_bounds__(TRI ? EVR_FAST_MAX_THREADS_TRI : EVR_FAST_MAX_THREADS, 1)
 sg4_term_kernel_fast(const FastPlanDev P, const FastClassDev Cc, const int npsi,
                      const double *__restrict__ psi, double *__restrict__ Hpsi)
 {
@@ -450,7 +657,7 @@ sg4_term_kernel_fast(const FastPlanDev P, const FastClassDev Cc, const int npsi,
             A.hasV = 0; A.fuse_g2b = 0; A.store_psi = 0; A.pool = mats;
             auto set_group = [&](int g) {
                 const FastGroup &Gr = T->g[g];
-                A.stride = Gr.stride; A.magic = Gr.magic; A.m1 = Gr.mat1; A.m2 = Gr.mat2;
+                A.stride = Gr.stride; A.magic = Gr.magic; A.m1 = Gr.mat1; A.m2 = Gr.mat2; A.m3 = Gr.mat3;
             };
             if (G == 0) {
                 if (tid < nb0) s_acc[tid] = (T->vshift + (hasV ? s_acc[tid] : 0.0)) * s_psi[tid];
@@ -458,24 +665,26 @@ sg4_term_kernel_fast(const FastPlanDev P, const FastClassDev Cc, const int npsi,
             } else {
                 for (int g = 0; g < G - 1; ++g) {                 // B -> G (BDP_TO_GDP_OF_SmolyakRep)
                     set_group(g);
-                    dispatch_pass<PASS_B2G, MS, RT, false, false, false>(T->g[g].tmpl, T->g[g].n1, A);
+                    dispatch_pass<PASS_B2G, MS, RT, TRI, false, false, false>(T->g[g].tmpl, T->g[g].n1, A);
                     group_sync(gsize, group);
                 }
                 // last group: B -> G, (V+shift) psi, its kinetic part (, its G -> B when it is the only group)
                 set_group(G - 1);
                 A.hasV = hasV ? 1 : 0;
-                A.fuse_g2b = (G == 1 && v_fused) ? 1 : 0;
+                const bool cube_last = T->g[G - 1].n3 > 0;
+                A.fuse_g2b = (G == 1 && v_fused && !cube_last) ? 1 : 0;
                 A.store_psi = (G > 1 || !v_fused) ? 1 : 0;
                 {
                     const int tm = T->g[G - 1].tmpl, n1 = T->g[G - 1].n1;
                     if (A.fuse_g2b) {            // single group, V fused: B->G, V, T, G->B in one pass
-                        if (A.hasV) dispatch_pass<PASS_LAST, MS, RT, true, true, false>(tm, n1, A);
-                        else dispatch_pass<PASS_LAST, MS, RT, false, true, false>(tm, n1, A);
+                        if (A.hasV) dispatch_pass<PASS_LAST, MS, RT, TRI, true, true, false>(tm, n1, A);
+                        else dispatch_pass<PASS_LAST, MS, RT, TRI, false, true, false>(tm, n1, A);
                     } else if (A.store_psi) {
-                        if (A.hasV) dispatch_pass<PASS_LAST, MS, RT, true, false, true>(tm, n1, A);
-                        else dispatch_pass<PASS_LAST, MS, RT, false, false, true>(tm, n1, A);
-                    } else {
-                        dispatch_pass<PASS_LAST, MS, RT, false, false, false>(tm, n1, A);
+                        if (A.hasV) dispatch_pass<PASS_LAST, MS, RT, TRI, true, false, true>(tm, n1, A);
+                        else dispatch_pass<PASS_LAST, MS, RT, TRI, false, false, true>(tm, n1, A);
+                    } else {                     // single cube group: G->B follows as a separate pass
+                        if (A.hasV) dispatch_pass<PASS_LAST, MS, RT, TRI, true, false, false>(tm, n1, A);
+                        else dispatch_pass<PASS_LAST, MS, RT, TRI, false, false, false>(tm, n1, A);
                     }
                 }
                 A.hasV = 0; A.store_psi = 0;
@@ -503,16 +712,16 @@ sg4_term_kernel_fast(const FastPlanDev P, const FastClassDev Cc, const int npsi,
                 for (int g = G - 2; g >= 0; --g) {
                     set_group(g);
                     A.fuse_g2b = (g == 0) ? 1 : 0;
-                    if (g == 0) dispatch_pass<PASS_KEO, MS, RT, false, true, false>(T->g[g].tmpl, T->g[g].n1, A);
-                    else dispatch_pass<PASS_KEO, MS, RT, false, false, false>(T->g[g].tmpl, T->g[g].n1, A);
+                    if (g == 0 && T->g[0].n3 == 0) dispatch_pass<PASS_KEO, MS, RT, TRI, false, true, false>(T->g[g].tmpl, T->g[g].n1, A);
+                    else dispatch_pass<PASS_KEO, MS, RT, TRI, false, false, false>(T->g[g].tmpl, T->g[g].n1, A);
                     group_sync(gsize, group);
                 }
                 A.fuse_g2b = 0;
                 // remaining G -> B (GDP_TO_BDP_OF_SmolyakRep)
-                const int g_first = (G == 1) ? (v_fused ? 1 : 0) : 1;
+                const int g_first = (T->g[0].n3 > 0) ? 0 : ((G == 1) ? (v_fused ? 1 : 0) : 1);
                 for (int g = g_first; g < G; ++g) {
                     set_group(g);
-                    dispatch_pass<PASS_G2B, MS, RT, false, false, false>(T->g[g].tmpl, T->g[g].n1, A);
+                    dispatch_pass<PASS_G2B, MS, RT, TRI, false, false, false>(T->g[g].tmpl, T->g[g].n1, A);
                     group_sync(gsize, group);
                 }
             }

@@ -71,9 +71,9 @@ struct evr_sg4_plan {
     int n_classes = 0;
     bool fast_pool_in_smem = false;
     bool fast_block_order = false;
-    evr::FastClassDev fclass[6];
-    size_t fclass_smem[6] = {0, 0, 0, 0, 0, 0};
-    int fclass_ctas[6] = {0, 0, 0, 0, 0, 0};
+    evr::FastClassDev fclass[9];
+    size_t fclass_smem[9] = {0};
+    int fclass_ctas[9] = {0};
     // device
     evr::TermDev *d_terms = nullptr;
     uint8_t *d_lev = nullptr;
@@ -84,8 +84,8 @@ struct evr_sg4_plan {
     double *d_psi = nullptr, *d_Hpsi = nullptr;   // staging for the host-buffer entry point
     int64_t stage_cap = 0;
     cudaStream_t stream = nullptr;
-    cudaStream_t side[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // class kernels overlap their tails
-    cudaEvent_t ev_fork = nullptr, ev_join[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaStream_t side[9] = {nullptr};   // class kernels overlap their tails
+    cudaEvent_t ev_fork = nullptr, ev_join[9] = {nullptr};
     size_t smem_bytes = 0;
     int grid_ctas = 0;
     evr::PlanDev pd{};
@@ -240,7 +240,7 @@ extern "C" int evr_sg4_plan_create(evr_sg4_plan **out, int device,
     }
     if (!getenv("EVR_SG4_SINGLE_STREAM")) {
         bool ok_ev = cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming) == cudaSuccess;
-        for (int c = 1; c < 6 && ok_ev; ++c)
+        for (int c = 1; c < 9 && ok_ev; ++c)
             ok_ev = cudaStreamCreateWithFlags(&p->side[c], cudaStreamNonBlocking) == cudaSuccess &&
                     cudaEventCreateWithFlags(&p->ev_join[c], cudaEventDisableTiming) == cudaSuccess;
         if (!ok_ev) { evr_sg4_plan_destroy(&p); return fail("evr_sg4_plan_create: side stream/event creation failed"); }
@@ -352,11 +352,31 @@ static int build_fast_path(evr_sg4_plan *p, int nb_Term, const int32_t *term_mod
             if (n > 1 && fast_template_id(n, 0) == 0) { term_rt[t] = 1; if (n > EVR_RT_NMAX) return 0; }
         }
     }
+    // size classes and threads per term (tunable for experiments: EVR_SG4_T0/T1 thresholds, EVR_SG4_G0/G1/G2 group sizes)
+    auto envi = [](const char *n, int d) { const char *v = getenv(n); return v ? atoi(v) : d; };
+    const int64_t thr0 = envi("EVR_SG4_T0", 1024), thr1 = envi("EVR_SG4_T1", 384);
+    // cube tiles (three equal modes of size 3 or 2 per thread): how many cubes minimise the group count of a term
+    const bool use_cubes = envi("EVR_SG4_CUBES", 0) != 0;
+    auto n_cubes = [](int c) { return (c == 3 || c == 5 || c == 6) ? c / 3 : (c >= 7 ? (c - 4) / 3 + ((c - 4) % 3 == 2 ? 0 : 0) + 1 : 0); };
+    std::vector<char> term_tri(p->n_terms, 0);
+    if (use_cubes)
+        for (int t = 0; t < p->n_terms; ++t) {
+            if (term_rt[t]) continue;
+            const int iG = p->iG_begin + t;
+            int c3 = 0, c2 = 0;
+            for (int k = 0; k < D; ++k) {
+                const int n = p->h_nq_of[k * (LG + 1) + p->h_tab_l[(size_t)iG * D + k]];
+                c3 += (n == 3); c2 += (n == 2);
+            }
+            if (n_cubes(c3) > 0 || n_cubes(c2) > 0) term_tri[t] = 1;
+        }
     auto class_of = [&](int t) {
         const int64_t sz = (int64_t)p->h_tab_nq[p->iG_begin + t] * nb0;
-        return (sz > 1024 ? 0 : (sz > 384 ? 1 : 2)) + (term_rt[t] ? 3 : 0);
+        return (sz > thr0 ? 0 : (sz > thr1 ? 1 : 2)) + (term_rt[t] ? 3 : (term_tri[t] ? 6 : 0));
     };
-    static const int class_gsize[6] = {128, 64, 32, 128, 64, 32};
+    const int class_gsize[9] = {envi("EVR_SG4_G0", 128), envi("EVR_SG4_G1", 64), envi("EVR_SG4_G2", 32),
+                                envi("EVR_SG4_G0", 128), envi("EVR_SG4_G1", 64), envi("EVR_SG4_G2", 32),
+                                envi("EVR_SG4_G0T", 64), envi("EVR_SG4_G1T", 32), envi("EVR_SG4_G2T", 32)};
     std::vector<int> forder(p->n_terms);
     std::iota(forder.begin(), forder.end(), 0);
     std::stable_sort(forder.begin(), forder.end(), [&](int a, int b) {
@@ -419,14 +439,30 @@ static int build_fast_path(evr_sg4_plan *p, int nb_Term, const int32_t *term_mod
             refstride *= n;
         }
         std::stable_sort(act.begin(), act.end(), [](const Act &a, const Act &b) { return a.n < b.n; });
-        struct Grp { int a1, a2; };            // indices into act; a2 = -1 single
+        struct Grp { int a1, a2, a3; };        // indices into act; a2 = -1 single; a3 >= 0 cube
         std::vector<Grp> grp;
-        int lo = 0, hi = (int)act.size() - 1;
-        while (lo <= hi) {
-            if (!term_rt[t] && lo < hi && fast_pair_supported(act[lo].n, act[hi].n)) { grp.push_back({lo, hi}); ++lo; --hi; }
-            else { grp.push_back({hi, -1}); --hi; }
+        std::vector<char> used(act.size(), 0);
+        if (term_tri[t]) {                     // cubes of equal size-3 (or size-2) modes first
+            for (int sz : {3, 2}) {
+                std::vector<int> idxs;
+                for (size_t a = 0; a < act.size(); ++a) if (act[a].n == sz) idxs.push_back((int)a);
+                int nc = n_cubes((int)idxs.size());
+                for (int c = 0; c < nc; ++c) {
+                    grp.push_back({idxs[3 * c], idxs[3 * c + 1], idxs[3 * c + 2]});
+                    used[idxs[3 * c]] = used[idxs[3 * c + 1]] = used[idxs[3 * c + 2]] = 1;
+                }
+            }
         }
-        auto gsize = [&](const Grp &g) { return act[g.a1].n * (g.a2 >= 0 ? act[g.a2].n : 1); };
+        {
+            std::vector<int> rest;
+            for (size_t a = 0; a < act.size(); ++a) if (!used[a]) rest.push_back((int)a);
+            int lo = 0, hi = (int)rest.size() - 1;
+            while (lo <= hi) {
+                if (!term_rt[t] && lo < hi && fast_pair_supported(act[rest[lo]].n, act[rest[hi]].n)) { grp.push_back({rest[lo], rest[hi], -1}); ++lo; --hi; }
+                else { grp.push_back({rest[hi], -1, -1}); --hi; }
+            }
+        }
+        auto gsize = [&](const Grp &g) { return act[g.a1].n * (g.a2 >= 0 ? act[g.a2].n : 1) * (g.a3 >= 0 ? act[g.a3].n : 1); };
         std::stable_sort(grp.begin(), grp.end(), [&](const Grp &a, const Grp &b) { return gsize(a) > gsize(b); });
         if ((int)grp.size() > EVR_MAXG) { ok = false; continue; }
         F.ngroups = (int)grp.size();
@@ -452,7 +488,16 @@ static int build_fast_path(evr_sg4_plan *p, int nb_Term, const int32_t *term_mod
                 in_n.push_back(A2.n); in_ref.push_back(A2.refstride);
                 stride *= A2.n;
             } else { Gd.n2 = 0; Gd.mat2 = Gd.mat1; }
-            Gd.tmpl = term_rt[t] ? 0 : (unsigned short)fast_template_id(Gd.n1, Gd.n2);
+            Gd.n3 = 0; Gd.mat3 = Gd.mat1;
+            if (grp[g].a3 >= 0) {
+                const Act &A3 = act[grp[g].a3];
+                Gd.n3 = (unsigned short)A3.n;
+                const int l3 = p->h_tab_l[(size_t)iG * D + A3.k];
+                Gd.mat3 = moff[A3.k * (LG + 1) + l3];
+                in_n.push_back(A3.n); in_ref.push_back(A3.refstride);
+                stride *= A3.n;
+            }
+            Gd.tmpl = term_rt[t] ? 0 : (Gd.n3 == 3 ? EVR_TMPL_CUBE3 : (Gd.n3 == 2 ? EVR_TMPL_CUBE2 : (unsigned short)fast_template_id(Gd.n1, Gd.n2)));
             if (!term_rt[t] && Gd.tmpl == 0) ok = false;
         }
         // permutation: internal index q' -> reference index q (odometer over internal modes)
@@ -485,26 +530,30 @@ static int build_fast_path(evr_sg4_plan *p, int nb_Term, const int32_t *term_mod
     }
     if (!ok) return 0;
     // launch configuration per size class + "next term" prefetch links
-    CUDA_TRY(cudaFuncSetAttribute(evr::sg4_term_kernel_fast<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    CUDA_TRY(cudaFuncSetAttribute(evr::sg4_term_kernel_fast<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    CUDA_TRY(cudaFuncSetAttribute(evr::sg4_term_kernel_fast<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    CUDA_TRY(cudaFuncSetAttribute(evr::sg4_term_kernel_fast<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CUDA_TRY(cudaFuncSetAttribute(evr::sg4_term_kernel_fast<true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CUDA_TRY(cudaFuncSetAttribute(evr::sg4_term_kernel_fast<false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CUDA_TRY(cudaFuncSetAttribute(evr::sg4_term_kernel_fast<true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CUDA_TRY(cudaFuncSetAttribute(evr::sg4_term_kernel_fast<false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CUDA_TRY(cudaFuncSetAttribute(evr::sg4_term_kernel_fast<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CUDA_TRY(cudaFuncSetAttribute(evr::sg4_term_kernel_fast<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     p->n_classes = 0;
     {
         int w0 = 0;
-        for (int c = 0; c < 6; ++c) {
+        for (int c = 0; c < 9; ++c) {
             int w1 = w0;
             int64_t cap = 1;
             while (w1 < p->n_terms && class_of(forder[w1]) == c) { cap = std::max<int64_t>(cap, (int64_t)fterms[w1].nq * nb0); ++w1; }
             if (w1 == w0) continue;
-            const bool rt = (c >= 3);
+            const bool rt = (c >= 3 && c < 6), tri = (c >= 6);
             const int gsize = class_gsize[c];
+            const int max_threads = tri ? EVR_FAST_MAX_THREADS_TRI : EVR_FAST_MAX_THREADS;
             const size_t per_group = (size_t)2 * cap * sizeof(double) + 2 * sizeof(evr::FastTermDev);
             const size_t pool_bytes = pool_in_smem ? pool.size() * sizeof(double) : 0;
             const size_t budget = 227 * 1024;
             if (pool_bytes + per_group > budget) return 0;
-            int ngrp = (int)std::min<size_t>((budget - pool_bytes) / per_group, (size_t)(EVR_FAST_MAX_THREADS / gsize));
+            int ngrp = (int)std::min<size_t>((budget - pool_bytes) / per_group, (size_t)(max_threads / gsize));
             if (gsize > 32) ngrp = std::min(ngrp, 15);          // named barriers 1..15
+            if (envi("EVR_SG4_GRP_PCT", 100) < 100) ngrp = std::max(1, ngrp * envi("EVR_SG4_GRP_PCT", 100) / 100);   // experiment
             ngrp = std::max(1, std::min(ngrp, (w1 - w0 + p->sm_count - 1) / p->sm_count));
             const size_t smem = pool_bytes + per_group * ngrp;
             const int n = w1 - w0;
@@ -518,7 +567,7 @@ static int build_fast_path(evr_sg4_plan *p, int nb_Term, const int32_t *term_mod
                 else { F.next2_map_off = 0; F.next2_nq = 0; }
             }
             evr::FastClassDev &C = p->fclass[p->n_classes];
-            C.term_begin = w0; C.n_terms = n; C.gsize = gsize; C.rt = rt ? 1 : 0; C.cap = (int)cap; C.cta_threads = ngrp * gsize;
+            C.term_begin = w0; C.n_terms = n; C.gsize = gsize; C.rt = rt ? 1 : 0; C.tri = tri ? 1 : 0; C.cap = (int)cap; C.cta_threads = ngrp * gsize;
             p->fclass_smem[p->n_classes] = smem; p->fclass_ctas[p->n_classes] = ctas;
             ++p->n_classes;
             w0 = w1;
@@ -641,15 +690,15 @@ static int launch(evr_sg4_plan *p, int npsi, const double *d_psi_user, double *d
                 cudaStream_t st_main = st;
                 cudaStream_t st = (multi && c > 0) ? p->side[c] : st_main;
                 if (multi && c > 0) CUDA_TRY(cudaStreamWaitEvent(st, p->ev_fork, 0));
-                const bool ms = p->fast_pool_in_smem, rt = p->fclass[c].rt != 0;
-                if (ms && !rt)
-                    evr::sg4_term_kernel_fast<true, false><<<p->fclass_ctas[c], p->fclass[c].cta_threads, p->fclass_smem[c], st>>>(p->fpd, p->fclass[c], npsi, d_psi, d_Hpsi);
-                else if (!ms && !rt)
-                    evr::sg4_term_kernel_fast<false, false><<<p->fclass_ctas[c], p->fclass[c].cta_threads, p->fclass_smem[c], st>>>(p->fpd, p->fclass[c], npsi, d_psi, d_Hpsi);
-                else if (ms)
-                    evr::sg4_term_kernel_fast<true, true><<<p->fclass_ctas[c], p->fclass[c].cta_threads, p->fclass_smem[c], st>>>(p->fpd, p->fclass[c], npsi, d_psi, d_Hpsi);
-                else
-                    evr::sg4_term_kernel_fast<false, true><<<p->fclass_ctas[c], p->fclass[c].cta_threads, p->fclass_smem[c], st>>>(p->fpd, p->fclass[c], npsi, d_psi, d_Hpsi);
+                const bool ms = p->fast_pool_in_smem, rt = p->fclass[c].rt != 0, tri = p->fclass[c].tri != 0;
+                const int nctas = p->fclass_ctas[c], nthr = p->fclass[c].cta_threads;
+                const size_t sm = p->fclass_smem[c];
+                if (tri && ms)       evr::sg4_term_kernel_fast<true, false, true><<<nctas, nthr, sm, st>>>(p->fpd, p->fclass[c], npsi, d_psi, d_Hpsi);
+                else if (tri)        evr::sg4_term_kernel_fast<false, false, true><<<nctas, nthr, sm, st>>>(p->fpd, p->fclass[c], npsi, d_psi, d_Hpsi);
+                else if (ms && !rt)  evr::sg4_term_kernel_fast<true, false, false><<<nctas, nthr, sm, st>>>(p->fpd, p->fclass[c], npsi, d_psi, d_Hpsi);
+                else if (!ms && !rt) evr::sg4_term_kernel_fast<false, false, false><<<nctas, nthr, sm, st>>>(p->fpd, p->fclass[c], npsi, d_psi, d_Hpsi);
+                else if (ms)         evr::sg4_term_kernel_fast<true, true, false><<<nctas, nthr, sm, st>>>(p->fpd, p->fclass[c], npsi, d_psi, d_Hpsi);
+                else                 evr::sg4_term_kernel_fast<false, true, false><<<nctas, nthr, sm, st>>>(p->fpd, p->fclass[c], npsi, d_psi, d_Hpsi);
                 p->launches += 1;
                 if (multi && c > 0) {
                     CUDA_TRY(cudaEventRecord(p->ev_join[c], st));
@@ -737,7 +786,7 @@ extern "C" int evr_sg4_plan_destroy(evr_sg4_plan **pp)
     cudaFree(p->d_fterms); cudaFree(p->d_fmap); cudaFree(p->d_fmats); cudaFree(p->d_fV);
     cudaFree(p->d_fpos); cudaFree(p->d_perm); cudaFree(p->d_psi_int); cudaFree(p->d_Hpsi_int);
     if (p->stream) cudaStreamDestroy(p->stream);
-    for (int c = 0; c < 6; ++c) { if (p->side[c]) cudaStreamDestroy(p->side[c]); if (p->ev_join[c]) cudaEventDestroy(p->ev_join[c]); }
+    for (int c = 0; c < 9; ++c) { if (p->side[c]) cudaStreamDestroy(p->side[c]); if (p->ev_join[c]) cudaEventDestroy(p->ev_join[c]); }
     if (p->ev_fork) cudaEventDestroy(p->ev_fork);
     delete p;
     *pp = nullptr;
