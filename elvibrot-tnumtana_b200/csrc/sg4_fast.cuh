@@ -582,24 +582,29 @@ sg4_term_kernel_fast(const FastPlanDev P, const FastClassDev Cc, const int npsi,
     const bool v_fused = (nb0 == 1);
     const bool hasV = v_fused && P.has_V;
 
-    const int it_first = blockIdx.x * ngrp + group;
-    if (it_first < Cc.n_terms) {   // first descriptor of this group
-        const double *src = reinterpret_cast<const double *>(terms + it_first);
+    // work item = (term, right-hand side), item w -> term w / npsi, RHS w % npsi: blocks of vectors (Davidson)
+    // keep every thread group busy even when the configuration has few Smolyak terms
+    const long long n_items = (long long)Cc.n_terms * npsi;
+    const long long w_first = blockIdx.x * ngrp + group;
+    if (w_first < n_items) {   // first descriptor of this group
+        const double *src = reinterpret_cast<const double *>(terms + (int)(w_first / npsi));
         double *dst = reinterpret_cast<double *>(s_T0);
         for (int i = tid; i < (int)(sizeof(FastTermDev) / 8); i += gsize) cp_async8(dst + i, src + i);
     }
     int ts = 0;
-    for (int it = it_first; it < Cc.n_terms; it += step, ts ^= 1) {
-        cp_async_commit_wait_all();            // descriptor of this term has landed (issued one term ago)
+    for (long long w = w_first; w < n_items; w += step, ts ^= 1) {
+        const int it = (int)(w / npsi);
+        const int ip = (int)(w - (long long)it * npsi);
+        cp_async_commit_wait_all();            // descriptor of this item has landed (issued one item ago)
         group_sync(gsize, group);
-        if (it + step < Cc.n_terms) {          // descriptor of the next term -> other slot, asynchronously
-            const double *src = reinterpret_cast<const double *>(terms + it + step);
+        if (w + step < n_items) {              // descriptor of the next item -> other slot, asynchronously
+            const double *src = reinterpret_cast<const double *>(terms + (int)((w + step) / npsi));
             double *dst = reinterpret_cast<double *>(s_T0 + (ts ^ 1));
             for (int i = tid; i < (int)(sizeof(FastTermDev) / 8); i += gsize) cp_async8(dst + i, src + i);
         }
         const FastTermDev *T = s_T0 + ts;
         const int G = (P.dbg & 4) ? 0 : T->ngroups, nq = T->nq;
-        if (T->next_nq > 0) {   // pull the next term's mapping / V slices and descriptor into L2
+        if (npsi == 1 && T->next_nq > 0) {   // pull the next term's mapping / V slices into L2 (links assume npsi = 1)
             const char *pm = reinterpret_cast<const char *>(P.map + T->next_map_off);
             for (int b = tid * 128; b < T->next_nq * 4; b += gsize * 128) prefetch_l2(pm + b);
             const char *pq = reinterpret_cast<const char *>(P.pos + T->next_map_off);
@@ -613,7 +618,7 @@ sg4_term_kernel_fast(const FastPlanDev P, const FastClassDev Cc, const int npsi,
         const uint16_t *pp = P.pos + T->map_off;
         const double *Vt = P.has_V ? P.V + T->grid_off : nullptr;
 
-        for (int ip = 0; ip < npsi; ++ip) {
+        {
             const double *x = psi + (long long)ip * nvec;
             double *y = Hpsi + (long long)ip * nvec;
             // gather (tabPackedBasis_TO_tabR_AT_iG); V of the term goes to the acc buffer, where the

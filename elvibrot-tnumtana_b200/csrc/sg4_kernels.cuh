@@ -104,7 +104,12 @@ sg4_term_kernel_generic(const PlanDev P, const int npsi,
     const int D = P.D, nb0 = P.nb0;
     const long long nvec = P.nb * nb0;
 
-    for (int it = blockIdx.x; it < P.n_terms; it += gridDim.x) {
+    // work item = (term, right-hand side): blocks of RHS (Davidson) fill the GPU even when a configuration has
+    // few Smolyak terms (HCN_UT: 85 terms x 27 vectors)
+    const long long n_items = (long long)P.n_terms * npsi;
+    for (long long w = blockIdx.x; w < n_items; w += gridDim.x) {
+        const int it = (int)(w / npsi);
+        const int ip_only = (int)(w - (long long)it * npsi);
         const TermDev T = P.terms[it];
         const uint8_t *lev = P.lev + T.lev_off;
         __syncthreads();               // previous term fully done before the per-term tables change
@@ -121,7 +126,7 @@ sg4_term_kernel_generic(const PlanDev P, const int npsi,
         const int nq = T.nq, nbT = T.nbT;
         const int32_t *mp = P.map + T.map_off;
 
-        for (int ip = 0; ip < npsi; ++ip) {
+        for (int ip = ip_only; ip <= ip_only; ++ip) {
             const double *x = psi + (long long)ip * nvec;
             double *y = Hpsi + (long long)ip * nvec;
             // ---- gather

@@ -87,7 +87,7 @@ struct evr_sg4_plan {
     cudaStream_t side[9] = {nullptr};   // class kernels overlap their tails
     cudaEvent_t ev_fork = nullptr, ev_join[9] = {nullptr};
     size_t smem_bytes = 0;
-    int grid_ctas = 0;
+    int grid_ctas = 0, gen_ctas_max = 0;
     evr::PlanDev pd{};
 };
 
@@ -256,6 +256,7 @@ extern "C" int evr_sg4_plan_create(evr_sg4_plan **out, int device,
         evr_sg4_plan_destroy(&p); return fail("evr_sg4_plan_create: kernel cannot be resident (occupancy 0)");
     }
     p->grid_ctas = std::max(1, std::min(p->n_terms, p->sm_count * occ));
+    p->gen_ctas_max = p->sm_count * occ;
 
     evr::PlanDev &pd = p->pd;
     pd.D = D; pd.LG = LG; pd.nb0 = nb0; pd.n_terms = p->n_terms; pd.nb = nb; pd.NQ_local = p->NQ_local;
@@ -706,7 +707,9 @@ static int launch(evr_sg4_plan *p, int npsi, const double *d_psi_user, double *d
                 }
             }
         } else {
-            evr::sg4_term_kernel_generic<<<p->grid_ctas, 256, p->smem_bytes, st>>>(p->pd, npsi, d_psi, d_Hpsi);
+            const long long items = (long long)p->n_terms * npsi;
+            const int ctas = (int)std::max<long long>(1, std::min<long long>(items, (long long)p->gen_ctas_max));
+            evr::sg4_term_kernel_generic<<<ctas, 256, p->smem_bytes, st>>>(p->pd, npsi, d_psi, d_Hpsi);
             p->launches += 1;
         }
         CUDA_TRY(cudaGetLastError());
