@@ -5,9 +5,9 @@ layout); import it with ``importlib.import_module("elvibrot-tnumtana_b200")`` or
 """
 from . import distributed, lib, primitives, sg4, workloads  # noqa: F401
 from .lib import EvrSg4Error, build  # noqa: F401
-from .sg4 import (Basis_L_TO_n, EvrStop, Init_TypeOp, OpGrid, ParamOp, ParamPsi, SG4Basis,  # noqa: F401
+from .sg4 import (Basis_L_TO_n, EvrStop, Init_TypeOp, OpGrid, ParamOp, ParamOp10, ParamPsi, SG4Basis,  # noqa: F401
                   level_sizes, sub_OpPsi, sub_scaledOpPsi, sub_TabOpPsi, sub_TabOpPsi_FOR_SGtype4)
 
 __all__ = ["distributed", "lib", "primitives", "sg4", "workloads", "build", "EvrSg4Error", "EvrStop", "Basis_L_TO_n",
-           "Init_TypeOp", "OpGrid", "ParamOp", "ParamPsi", "SG4Basis", "level_sizes", "sub_OpPsi",
+           "Init_TypeOp", "OpGrid", "ParamOp", "ParamOp10", "ParamPsi", "SG4Basis", "level_sizes", "sub_OpPsi",
            "sub_scaledOpPsi", "sub_TabOpPsi", "sub_TabOpPsi_FOR_SGtype4"]

@@ -247,3 +247,174 @@ sg4_term_kernel_generic(const PlanDev P, const int npsi,
 }
 
 } // namespace evr
+
+namespace evr {
+
+// ---- type_Op = 10 with the metric tensor cached on the device --------------------------
+// H psi = -1/2 (Jac sq)^-1 sum_i d_i [ Jac sum_j G^{ji} d_j (sq psi) ] + V psi,  sq = sqrt(rho/Jac)
+// ref: sub_TabOpPsi_OF_ONEDP_FOR_SGtype4 CASE (10), sub_Operator/sub_OpPsi_SG4.f90:1548-1650; the reference
+// recomputes G(Q) with Tnum at every grid point of every call (:2717-2728), here G, Jac and sq are plan data.
+struct Op10Dev {
+    int n_act;                   // number of active coordinates
+    int act_mode[EVR_MAXD];      // 0-based SG4 mode owning active coordinate j
+    int has_V;
+    int nqmax;                   // largest term grid of the plan's range
+    const double *V;             // [nb0*nb0][NQ_local]
+    const double *GG;            // [n_act*n_act][NQ_local]   GG[(j + n*i)*NQ + q] = GGiq(q,j,i)
+    const double *Jac, *sq;      // [NQ_local]
+};
+
+#define EVR_OP10_PTS 8           // grid points per thread kept in registers (nq <= 8*256)
+
+// dynamic smem: bufA[cap] | bufB[cap] | R[n_act][nqmax] | chi[nqmax] | ints (as the generic kernel)
+__global__ void __launch_bounds__(256)
+sg4_term_kernel_type10(const PlanDev P, const Op10Dev O, const int npsi,
+                       const double *__restrict__ psi, double *__restrict__ Hpsi)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double *bufA = reinterpret_cast<double *>(smem_raw);
+    double *bufB = bufA + P.cap;
+    double *sR   = bufB + P.cap;
+    double *chi  = sR + (size_t)O.n_act * O.nqmax;
+    int *s_nq_of = reinterpret_cast<int *>(chi + O.nqmax);
+    const int nT = P.D * (P.LG + 1);
+    int *s_nb_of = s_nq_of + nT;
+    int *s_offB  = s_nb_of + nT;
+    int *s_offG  = s_offB + nT;
+    int *s_tnq   = s_offG + nT;
+    int *s_tnb   = s_tnq + P.D;
+    int *s_oB    = s_tnb + P.D;
+    int *s_oG    = s_oB + P.D;
+    int *s_str   = s_oG + P.D;
+
+    for (int i = threadIdx.x; i < nT; i += blockDim.x) {
+        s_nq_of[i] = P.nq_of[i]; s_nb_of[i] = P.nb_of[i];
+        s_offB[i] = P.offB[i];   s_offG[i] = P.offG[i];
+    }
+    __syncthreads();
+    const int D = P.D, nb0 = P.nb0, n = O.n_act;
+    const long long nvec = P.nb * nb0;
+    const long long n_items = (long long)P.n_terms * npsi;
+
+    for (long long w = blockIdx.x; w < n_items; w += gridDim.x) {
+        const int it = (int)(w / npsi);
+        const int ip = (int)(w - (long long)it * npsi);
+        const TermDev T = P.terms[it];
+        const uint8_t *lev = P.lev + T.lev_off;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int str = 1;
+            for (int k = 0; k < D; ++k) {
+                const int i = k * (P.LG + 1) + lev[k];
+                s_tnq[k] = s_nq_of[i]; s_tnb[k] = s_nb_of[i];
+                s_oB[k] = s_offB[i];   s_oG[k] = s_offG[i];
+                s_str[k] = str; str *= s_nq_of[i];
+            }
+        }
+        __syncthreads();
+        const int nq = T.nq, nbT = T.nbT;
+        const int32_t *mp = P.map + T.map_off;
+        const double *x = psi + (long long)ip * nvec;
+        double *y = Hpsi + (long long)ip * nvec;
+        for (int j = threadIdx.x; j < nbT; j += blockDim.x) {
+            const int m = mp[j];
+            for (int c = 0; c < nb0; ++c)
+                bufA[c * nbT + j] = (m > 0) ? __ldg(x + (long long)c * P.nb + (m - 1)) : 0.0;
+        }
+        __syncthreads();
+        double *cur = bufA, *oth = bufB;
+        {   // B -> G
+            int left = 1, right = nbT * nb0;
+            for (int k = 0; k < D; ++k) {
+                const int nbk = s_tnb[k], nqk = s_tnq[k];
+                right /= nbk;
+                if (nbk == 1 && nqk == 1) {
+                    const double s = __ldg(P.B + s_oB[k]);
+                    const int total = left * right;
+                    for (int o = threadIdx.x; o < total; o += blockDim.x) cur[o] *= s;
+                } else {
+                    mode_product(P.B + s_oB[k], nqk, nbk, cur, oth, left, right);
+                    double *t = cur; cur = oth; oth = t;
+                }
+                left *= nqk;
+                __syncthreads();
+            }
+        }
+        const double *Jq = O.Jac + T.grid_off, *Sq = O.sq + T.grid_off;
+        // derivative of a grid array along the mode owning active coordinate a, at point q
+        auto deriv = [&](const double *arr, int a, int q) {
+            const int k = O.act_mode[a];
+            const double *M = P.D1 + s_oG[k];
+            const int nk = s_tnq[k], st = s_str[k];
+            const int qk = (q / st) % nk;
+            const int base = q - qk * st;
+            double s = 0.0;
+            for (int b = 0; b < nk; ++b) s = fma(__ldg(M + qk + nk * b), arr[base + b * st], s);
+            return s;
+        };
+        for (int c = 0; c < nb0; ++c) {
+            // phi = psi_c * sq  -> chi buffer
+            for (int q = threadIdx.x; q < nq; q += blockDim.x) chi[q] = cur[c * nq + q] * __ldg(Sq + q);
+            __syncthreads();
+            for (int a = 0; a < n; ++a)
+                for (int q = threadIdx.x; q < nq; q += blockDim.x) sR[(size_t)a * O.nqmax + q] = deriv(chi, a, q);
+            __syncthreads();
+            double acc[EVR_OP10_PTS];
+#pragma unroll
+            for (int u = 0; u < EVR_OP10_PTS; ++u) acc[u] = 0.0;
+            for (int i = 0; i < n; ++i) {
+                for (int q = threadIdx.x; q < nq; q += blockDim.x) {
+                    double s = 0.0;
+                    for (int j = 0; j < n; ++j)
+                        s = fma(__ldg(O.GG + (long long)(j + n * i) * P.NQ_local + T.grid_off + q), sR[(size_t)j * O.nqmax + q], s);
+                    chi[q] = s * __ldg(Jq + q);
+                }
+                __syncthreads();
+#pragma unroll
+                for (int u = 0; u < EVR_OP10_PTS; ++u) {
+                    const int q = threadIdx.x + u * blockDim.x;
+                    if (q < nq) acc[u] += deriv(chi, i, q);
+                }
+                __syncthreads();
+            }
+#pragma unroll
+            for (int u = 0; u < EVR_OP10_PTS; ++u) {
+                const int q = threadIdx.x + u * blockDim.x;
+                if (q < nq) {
+                    double r = -0.5 * acc[u] / (__ldg(Jq + q) * __ldg(Sq + q));
+                    if (O.has_V)
+                        for (int j = 0; j < nb0; ++j)
+                            r = fma(__ldg(O.V + (long long)(c + nb0 * j) * P.NQ_local + T.grid_off + q), cur[j * nq + q], r);
+                    oth[c * nq + q] = r;
+                }
+            }
+        }
+        __syncthreads();
+        { double *t = cur; cur = oth; oth = t; }
+        {   // G -> B
+            int left = 1, right = nq * nb0;
+            for (int k = 0; k < D; ++k) {
+                const int nbk = s_tnb[k], nqk = s_tnq[k];
+                right /= nqk;
+                if (nbk == 1 && nqk == 1) {
+                    const double s = __ldg(P.BTw + s_oB[k]);
+                    const int total = left * right;
+                    for (int o = threadIdx.x; o < total; o += blockDim.x) cur[o] *= s;
+                } else {
+                    mode_product(P.BTw + s_oB[k], nbk, nqk, cur, oth, left, right);
+                    double *t = cur; cur = oth; oth = t;
+                }
+                left *= nbk;
+                __syncthreads();
+            }
+        }
+        for (int j = threadIdx.x; j < nbT; j += blockDim.x) {
+            const int m = mp[j];
+            if (m > 0)
+                for (int c = 0; c < nb0; ++c)
+                    atomicAdd(y + (long long)c * P.nb + (m - 1), T.weight * cur[c * nbT + j]);
+        }
+    }
+}
+
+} // namespace evr

@@ -82,6 +82,12 @@ struct evr_sg4_plan {
     evr::OpTermDev *d_opterms = nullptr;
     double *d_grids = nullptr;
     double *d_psi = nullptr, *d_Hpsi = nullptr;   // staging for the host-buffer entry point
+    // type_Op = 10
+    bool op10 = false;
+    evr::Op10Dev o10{};
+    double *d_GG = nullptr, *d_Jac = nullptr, *d_sq = nullptr;
+    size_t smem10 = 0;
+    int ctas10_max = 0;
     int64_t stage_cap = 0;
     cudaStream_t stream = nullptr;
     cudaStream_t side[9] = {nullptr};   // class kernels overlap their tails
@@ -599,7 +605,7 @@ extern "C" int evr_sg4_plan_set_op(evr_sg4_plan *p, int type_Op, int nb_Term, co
 {
     if (!p) return fail("evr_sg4_plan_set_op: null plan");
     if (type_Op != 0 && type_Op != 1)
-        return fail("evr_sg4_plan_set_op: type_Op must be 0 or 1 (type_Op=10 is not built yet)");
+        return fail("evr_sg4_plan_set_op: type_Op must be 0 or 1 (use evr_sg4_plan_set_op10 for type_Op=10)");
     if (nb_Term < 1 || !grid_zero || !grid_cte) return fail("evr_sg4_plan_set_op: bad term list");
     if (type_Op == 1 && !term_mode) return fail("evr_sg4_plan_set_op: term_mode required for type_Op=1");
     CUDA_TRY(cudaSetDevice(p->device));
@@ -641,6 +647,7 @@ extern "C" int evr_sg4_plan_set_op(evr_sg4_plan *p, int type_Op, int nb_Term, co
             CUDA_TRY(cudaMemcpy(p->d_grids + (s * nb0 * nb0 + ij) * blk, src, (size_t)p->NQ_local * sizeof(double), cudaMemcpyHostToDevice));
         }
     if (upload(&p->d_opterms, ops.data(), ops.size())) return 1;
+    p->op10 = false;
     p->type_Op = type_Op; p->n_opterms = (int)ops.size(); p->n_var = (int)var_terms.size();
     p->pd.type_Op = type_Op; p->pd.n_opterms = p->n_opterms; p->pd.n_var = p->n_var;
     p->pd.opterms = p->d_opterms; p->pd.grids = p->d_grids;
@@ -658,6 +665,51 @@ extern "C" int evr_sg4_plan_set_op(evr_sg4_plan *p, int type_Op, int nb_Term, co
     p->flops_npsi1 += deriv_flops * nb0;
     if (build_fast_path(p, nb_Term, term_mode, grid_zero, grid_cte, Mat_cte, grids)) return 1;
     p->op_set = true;
+    return 0;
+}
+
+
+extern "C" int evr_sg4_plan_set_op10(evr_sg4_plan *p, int n_act, const int32_t *act_mode,
+                                     const double *V, const double *GG, const double *Jac, const double *sq)
+{
+    if (!p) return fail("evr_sg4_plan_set_op10: null plan");
+    if (n_act < 1 || n_act > EVR_MAXD || !act_mode || !GG || !Jac || !sq) return fail("evr_sg4_plan_set_op10: bad arguments");
+    CUDA_TRY(cudaSetDevice(p->device));
+    const int nb0 = p->nb0;
+    evr::Op10Dev &O = p->o10;
+    O.n_act = n_act;
+    for (int j = 0; j < n_act; ++j) {
+        if (act_mode[j] < 1 || act_mode[j] > p->D) return fail("evr_sg4_plan_set_op10: act_mode out of range");
+        O.act_mode[j] = act_mode[j] - 1;
+    }
+    int nqmax = 1;
+    for (int t = 0; t < p->n_terms; ++t) nqmax = std::max(nqmax, (int)p->h_tab_nq[p->iG_begin + t]);
+    if (nqmax > EVR_OP10_PTS * 256) return fail("evr_sg4_plan_set_op10: a Smolyak term has more than 2048 grid points (not supported for type_Op=10)");
+    O.nqmax = nqmax;
+    const int nT = p->D * (p->LG + 1);
+    p->smem10 = ((size_t)2 * p->cap + (size_t)(n_act + 1) * nqmax) * sizeof(double) + (size_t)(4 * nT + 5 * p->D) * sizeof(int);
+    if (p->smem10 > 227 * 1024) return fail("evr_sg4_plan_set_op10: shared-memory budget exceeded for this n_act / term size");
+    const size_t blk = (size_t)std::max<int64_t>(p->NQ_local, 1);
+    auto up_slice = [&](double **d, const double *h, int ncomp) -> int {
+        if (*d) { cudaFree(*d); *d = nullptr; }
+        CUDA_TRY(cudaMalloc((void **)d, blk * ncomp * sizeof(double)));
+        for (int c = 0; c < ncomp; ++c)
+            CUDA_TRY(cudaMemcpy(*d + (size_t)c * blk, h + (size_t)c * p->NQ_total + p->grid_start, (size_t)p->NQ_local * sizeof(double), cudaMemcpyHostToDevice));
+        return 0;
+    };
+    if (up_slice(&p->d_GG, GG, n_act * n_act)) return 1;
+    if (up_slice(&p->d_Jac, Jac, 1)) return 1;
+    if (up_slice(&p->d_sq, sq, 1)) return 1;
+    O.has_V = V ? 1 : 0;
+    if (V) { if (up_slice(&p->d_grids, V, nb0 * nb0)) return 1; }
+    O.V = p->d_grids; O.GG = p->d_GG; O.Jac = p->d_Jac; O.sq = p->d_sq;
+    CUDA_TRY(cudaFuncSetAttribute(evr::sg4_term_kernel_type10, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem10));
+    int occ = 0;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, evr::sg4_term_kernel_type10, 256, p->smem10));
+    if (occ < 1) return fail("evr_sg4_plan_set_op10: kernel cannot be resident");
+    p->ctas10_max = p->sm_count * occ;
+    p->type_Op = 10; p->pd.type_Op = 10; p->n_var = (V ? 1 : 0);
+    p->op10 = true; p->fast = false; p->op_set = true;
     return 0;
 }
 
@@ -706,6 +758,11 @@ static int launch(evr_sg4_plan *p, int npsi, const double *d_psi_user, double *d
                     CUDA_TRY(cudaStreamWaitEvent(st_main, p->ev_join[c], 0));
                 }
             }
+        } else if (p->op10) {
+            const long long items = (long long)p->n_terms * npsi;
+            const int ctas = (int)std::max<long long>(1, std::min<long long>(items, (long long)p->ctas10_max));
+            evr::sg4_term_kernel_type10<<<ctas, 256, p->smem10, st>>>(p->pd, p->o10, npsi, d_psi, d_Hpsi);
+            p->launches += 1;
         } else {
             const long long items = (long long)p->n_terms * npsi;
             const int ctas = (int)std::max<long long>(1, std::min<long long>(items, (long long)p->gen_ctas_max));
@@ -765,6 +822,7 @@ extern "C" int64_t evr_sg4_plan_info(const evr_sg4_plan *p, int what)
     switch (what) {
     case EVR_INFO_LAUNCHES: return p->launches;
     case EVR_INFO_ALG_BYTES_NPSI1:
+        if (p->op10) return p->S_local * nb0 * 8 * 2 + p->S_local * 4 * 2 + p->NQ_local * 8 * (nb0 * nb0 * p->n_var + p->o10.n_act * p->o10.n_act + 2) + p->nb * nb0 * 8 * 2;
         return p->S_local * nb0 * 8 * 2 + p->S_local * 4 * 2 + p->NQ_local * nb0 * nb0 * 8 * p->n_var + p->nb * nb0 * 8 * 2;
     case EVR_INFO_ALG_BYTES_PER_RHS_EXTRA:
         return p->S_local * nb0 * 8 * 2 + p->nb * nb0 * 8 * 2;
@@ -788,6 +846,7 @@ extern "C" int evr_sg4_plan_destroy(evr_sg4_plan **pp)
     cudaFree(p->d_opterms); cudaFree(p->d_grids); cudaFree(p->d_psi); cudaFree(p->d_Hpsi);
     cudaFree(p->d_fterms); cudaFree(p->d_fmap); cudaFree(p->d_fmats); cudaFree(p->d_fV);
     cudaFree(p->d_fpos); cudaFree(p->d_perm); cudaFree(p->d_psi_int); cudaFree(p->d_Hpsi_int);
+    cudaFree(p->d_GG); cudaFree(p->d_Jac); cudaFree(p->d_sq);
     if (p->stream) cudaStreamDestroy(p->stream);
     for (int c = 0; c < 9; ++c) { if (p->side[c]) cudaStreamDestroy(p->side[c]); if (p->ev_join[c]) cudaEventDestroy(p->ev_join[c]); }
     if (p->ev_fork) cudaEventDestroy(p->ev_fork);

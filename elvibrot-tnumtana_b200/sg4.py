@@ -261,6 +261,40 @@ class ParamOp:
         self.nb_OpPsi += npsi
 
 
+class ParamOp10(ParamOp):
+    """param_Op with type_Op = 10 and the metric tensor cached per grid point:
+    H = -1/2 (Jac sq)^-1 sum_i d_i [ Jac sum_j GG(:,j,i) d_j sq ] + V   (sub_OpPsi_SG4.f90:1548-1650).
+    GG(NQ,n,n), Jac(NQ), sqRhoOVERJac(NQ), V(NQ,nb0,nb0) or None: whole Smolyak grid, Fortran order."""
+
+    def __init__(self, BasisnD: SG4Basis, GG, Jac, sqRhoOVERJac, V=None, mode_of_Qact=None, iG_range=None, device: int = -1):
+        super().__init__(BasisnD, 10, [], mode_of_Qact=mode_of_Qact, iG_range=iG_range, device=device)
+        n = len(self.mode_of_Qact)
+        self.nb_act1 = n
+        self.GG = np.asfortranarray(np.asarray(GG, dtype=np.float64).reshape(BasisnD.nqq, n, n))
+        self.Jac = np.ascontiguousarray(Jac, dtype=np.float64)
+        self.sqRhoOVERJac = np.ascontiguousarray(sqRhoOVERJac, dtype=np.float64)
+        nb0 = BasisnD.nb0
+        self.V = None if V is None else np.asfortranarray(np.asarray(V, dtype=np.float64).reshape(BasisnD.nqq, nb0, nb0))
+
+    def _ensure_plan(self):
+        if self._plan:
+            return
+        b = self.BasisnD
+        L = _lib.lib()
+        _lib.check(L.evr_sg4_plan_create(
+            C.byref(self._plan), self.device, b.D, b.nb_SG, b.nb0, b.nb, b.LG,
+            b.nDind_SmolyakRep_Tab_nDval.ctypes.data, b.WeightSG.ctypes.data,
+            b.tab_nq_OF_SRep.ctypes.data, b.tab_nb_OF_SRep.ctypes.data, b.tab_iB_OF_SRep_TO_iB.ctypes.data,
+            b.nq_of.ctypes.data, b.nb_of.ctypes.data,
+            b.B.ctypes.data, b.BTw.ctypes.data, b.D1.ctypes.data, b.D2.ctypes.data,
+            int(self.iG_range[0]), int(self.iG_range[1])), "evr_sg4_plan_create")
+        am = np.ascontiguousarray(self.mode_of_Qact, dtype=np.int32)
+        _lib.check(L.evr_sg4_plan_set_op10(self._plan, len(am), am.ctypes.data,
+                                           None if self.V is None else self.V.ctypes.data,
+                                           self.GG.ctypes.data, self.Jac.ctypes.data, self.sqRhoOVERJac.ctypes.data),
+                   "evr_sg4_plan_set_op10")
+
+
 @dataclass
 class ParamPsi:
     """param_psi: packed basis representation, real (RvecB) or complex (CvecB)."""

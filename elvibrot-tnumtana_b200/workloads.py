@@ -20,7 +20,7 @@ from typing import List, Optional
 import numpy as np
 
 from .primitives import hm_primitive
-from .sg4 import Basis_L_TO_n, Init_TypeOp, OpGrid, ParamOp, SG4Basis, level_sizes
+from .sg4 import Basis_L_TO_n, Init_TypeOp, OpGrid, ParamOp, ParamOp10, SG4Basis, level_sizes
 
 LAMBDA_HH = 0.111803
 EV_TO_AU = 1.0 / 27.211386245988          # CODATA 2018 hartree energy in eV
@@ -179,3 +179,20 @@ def synthetic_curvilinear(basis: SG4Basis, seed: int = 777, iG_range=None, devic
                 g[:, c, c] = rng.standard_normal(NQ)
         ops.append(OpGrid((i, j), Grid=g))
     return ParamOp(basis, 1, ops, iG_range=iG_range, device=device)
+
+
+def synthetic_type10(basis: SG4Basis, seed: int = 777, with_V: bool = True, iG_range=None, device: int = -1):
+    """type_Op=10 operator with a synthetic, smoothly varying positive-definite metric tensor G(Q), Jacobian and
+    sqrt(rho/Jac) per grid point (shape-faithful stand-in for Tnum's get_d0GG output)."""
+    rng = np.random.default_rng(seed)
+    n, nb0, NQ = basis.D, basis.nb0, basis.nqq
+    A = 0.3 * rng.standard_normal((NQ, n, n))
+    GG = np.einsum("qij,qkj->qik", A, A) + np.eye(n)[None, :, :]          # SPD, symmetric
+    Jac = 1.0 + rng.random(NQ)
+    sq = 0.5 + rng.random(NQ)
+    V = None
+    if with_V:
+        V = rng.standard_normal((NQ, nb0, nb0))
+        V = 0.5 * (V + V.transpose(0, 2, 1))
+    return ParamOp10(basis, np.asfortranarray(GG), Jac, sq, V=None if V is None else np.asfortranarray(V),
+                     iG_range=iG_range, device=device)

@@ -116,6 +116,16 @@ int evr_sg4_plan_set_op(evr_sg4_plan *plan, int type_Op, int nb_Term,
                         const uint8_t *grid_zero, const uint8_t *grid_cte,
                         const double *Mat_cte, const double *const *grids);
 
+/* type_Op = 10 with the metric tensor cached per grid point (next row 8f-1 of SURVEY.md):
+ *   H psi = -1/2 (Jac sq)^-1 sum_i d_i [ Jac sum_j GG(:,j,i) d_j (sq psi) ] + V psi
+ * (sub_OpPsi_SG4.f90:1548-1650).  The reference recomputes GG/Jac/rho with Tnum at every grid point of every
+ * call (get_OpGrid_type10_OF_ONEDP_FOR_SG4, :2717-2728); here they are plan data, uploaded once.
+ *   act_mode[j]  1-based SG4 mode owning active coordinate j (liste_QactTOQdyn + Tabder_Qdyn_TO_Qbasis)
+ *   V            Grid(1:NQ,1:nb0,1:nb0) of the (0,0) term or NULL
+ *   GG           GGiq(1:NQ,1:n_act,1:n_act), Jac(1:NQ), sqRhoOVERJac(1:NQ), whole Smolyak grid, column-major. */
+int evr_sg4_plan_set_op10(evr_sg4_plan *plan, int n_act, const int32_t *act_mode,
+                          const double *V, const double *GG, const double *Jac, const double *sqRhoOVERJac);
+
 /* H|psi> for npsi real right-hand sides (complex psi = 2 real RHS, sub_OpPsi.f90:392-407).
  * psi/Hpsi[ipsi*nb*nb0 + ib0*nb + iB]  (= Psi(ipsi)%RvecB).  Hpsi is overwritten
  * (the reference zeroes it, sub_OpPsi_SG4.f90:765); with a term sub-range it holds

@@ -553,6 +553,165 @@ int orc_tab_oppsi(int D, int nb_SG, int nb0, int64_t nb, int LG,
     return 0;
 }
 
+/*
+ * type_Op = 10:  H = -1/2 J^-1 rho^-1/2 d_i [ J G^ij d_j ( rho^1/2 ... ) ] + V   with the metric tensor,
+ * Jacobian and sqrt(rho/J) CACHED per grid point (the reference recomputes G with Tnum at
+ * every call, get_OpGrid_type10_OF_ONEDP_FOR_SG4, sub_OpPsi_SG4.f90:2717-2728).
+ * ref: sub_TabOpPsi_OF_ONEDP_FOR_SGtype4, CASE (10), sub_OpPsi_SG4.f90:1548-1650:
+ *   VPsi(:,i) = sum_j V(:,i,j) psi(:,j)
+ *   per channel: phi = psi*sqRhoOVERJac ; phi_j = d/dQ_j phi ; chi_i = Jac * sum_j GG(:,j,i) phi_j ;
+ *                Op = -1/2 sum_i d/dQ_i chi_i / (Jac*sqRhoOVERJac) + VPsi
+ * act_mode[j] = 1-based SG4 mode owning active coordinate j.  V may be NULL (no potential).
+ * GG[iq + NQ*(j + n*i)] = GGiq(iq,j,i) on the whole Smolyak grid; Jac, sq: [NQ].
+ */
+int orc_tab_oppsi10(int D, int nb_SG, int nb0, int64_t nb, int LG,
+                    const int *tab_l, const double *W,
+                    const int *tab_nq, const int *tab_nb, const int32_t *map,
+                    const int *nq_of, const int *nb_of,
+                    const double *Bm, const double *BTw, const double *D1,
+                    int n_act, const int *act_mode,
+                    const double *V, const double *GG, const double *Jac, const double *sq,
+                    int npsi, const double *psi, double *Hpsi,
+                    int nthreads, int iG_begin, int iG_end, int zero_out)
+{
+    if (npsi < 1) return 1;
+    if (n_act < 1 || n_act > ORC_MAXD) return 2;
+    const int nT = D * (LG + 1);
+    int64_t *offB = (int64_t *)malloc(sizeof(int64_t) * nT);
+    int64_t *offG = (int64_t *)malloc(sizeof(int64_t) * nT);
+    table_offsets(D, LG, nq_of, nb_of, offB, offG);
+    int64_t *sum_nq = (int64_t *)malloc(sizeof(int64_t) * (nb_SG + 1));
+    int64_t *sum_nb = (int64_t *)malloc(sizeof(int64_t) * (nb_SG + 1));
+    sum_nq[0] = sum_nb[0] = 0;
+    int64_t maxn = 1;
+    for (int iG = 0; iG < nb_SG; ++iG) {
+        sum_nq[iG + 1] = sum_nq[iG] + tab_nq[iG];
+        sum_nb[iG + 1] = sum_nb[iG] + tab_nb[iG];
+        int64_t m = 1;
+        for (int k = 0; k < D; ++k) {
+            int l = tab_l[iG * D + k];
+            int a = nq_of[k * (LG + 1) + l], b = nb_of[k * (LG + 1) + l];
+            m *= (a > b) ? a : b;
+        }
+        if (m > maxn) maxn = m;
+    }
+    const int64_t NQ = sum_nq[nb_SG];
+    const int64_t nvec = nb * nb0;
+    if (zero_out) memset(Hpsi, 0, sizeof(double) * (size_t)nvec * npsi);
+    if (nthreads < 1) nthreads = 1;
+
+#pragma omp parallel num_threads(nthreads)
+    {
+        double *X    = (double *)malloc(sizeof(double) * (size_t)maxn);
+        double *Y    = (double *)malloc(sizeof(double) * (size_t)maxn);
+        double *Pg   = (double *)malloc(sizeof(double) * (size_t)maxn * nb0);
+        double *VPsi = (double *)malloc(sizeof(double) * (size_t)maxn * nb0);
+        double *Rj   = (double *)malloc(sizeof(double) * (size_t)maxn * n_act);
+        double *Ri   = (double *)malloc(sizeof(double) * (size_t)maxn);
+        double *Op   = (double *)malloc(sizeof(double) * (size_t)maxn);
+        int tnq[ORC_MAXD], tnb[ORC_MAXD], lk[ORC_MAXD];
+#pragma omp for schedule(static)
+        for (int iG = iG_begin; iG < iG_end; ++iG) {
+            const int nq = tab_nq[iG], nbT = tab_nb[iG];
+            for (int k = 0; k < D; ++k) {
+                lk[k] = tab_l[iG * D + k];
+                tnq[k] = nq_of[k * (LG + 1) + lk[k]];
+                tnb[k] = nb_of[k * (LG + 1) + lk[k]];
+            }
+            const int32_t *mp = map + sum_nb[iG];
+            const int64_t g0 = sum_nq[iG];
+            for (int ip = 0; ip < npsi; ++ip) {
+                const double *x = psi + (int64_t)ip * nvec;
+                double *y = Hpsi + (int64_t)ip * nvec;
+                for (int ib0 = 0; ib0 < nb0; ++ib0) {           /* gather + B -> G */
+                    for (int j = 0; j < nbT; ++j) {
+                        int32_t m = mp[j];
+                        X[j] = (m > 0 && m <= nb) ? x[(int64_t)ib0 * nb + m - 1] : 0.0;
+                    }
+                    double *a = X, *b = Y;
+                    int64_t left = 1, right = nbT;
+                    for (int k = 0; k < D; ++k) {
+                        right /= tnb[k];
+                        mode_apply(Bm + offB[k * (LG + 1) + lk[k]], tnq[k], tnb[k], a, b, left, right);
+                        left *= tnq[k];
+                        double *tmp = a; a = b; b = tmp;
+                    }
+                    memcpy(Pg + (int64_t)ib0 * nq, a, sizeof(double) * nq);
+                }
+                /* VPsi (:1578-1588) */
+                memset(VPsi, 0, sizeof(double) * (size_t)nq * nb0);
+                if (V)
+                    for (int ib0 = 0; ib0 < nb0; ++ib0)
+                        for (int jb0 = 0; jb0 < nb0; ++jb0) {
+                            const double *g = V + g0 + NQ * (ib0 + (int64_t)nb0 * jb0);
+                            for (int q = 0; q < nq; ++q) VPsi[(int64_t)ib0 * nq + q] += g[q] * Pg[(int64_t)jb0 * nq + q];
+                        }
+                for (int ib0 = 0; ib0 < nb0; ++ib0) {
+                    double *P = Pg + (int64_t)ib0 * nq;
+                    for (int q = 0; q < nq; ++q) P[q] *= sq[g0 + q];                    /* :1595 */
+                    for (int j = 0; j < n_act; ++j) {                                    /* :1602-1609 */
+                        double *dst = Rj + (int64_t)j * nq;
+                        memcpy(dst, P, sizeof(double) * nq);
+                        int64_t left = 1, right = nq;
+                        for (int k = 0; k < D; ++k) {
+                            right /= tnq[k];
+                            if (act_mode[j] == k + 1) {
+                                mode_apply(D1 + offG[k * (LG + 1) + lk[k]], tnq[k], tnq[k], dst, X, left, right);
+                                memcpy(dst, X, sizeof(double) * nq);
+                            }
+                            left *= tnq[k];
+                        }
+                    }
+                    memset(Op, 0, sizeof(double) * nq);
+                    for (int i = 0; i < n_act; ++i) {                                    /* :1613-1630 */
+                        memset(Ri, 0, sizeof(double) * nq);
+                        for (int j = 0; j < n_act; ++j) {
+                            const double *g = GG + g0 + NQ * (j + (int64_t)n_act * i);
+                            const double *r = Rj + (int64_t)j * nq;
+                            for (int q = 0; q < nq; ++q) Ri[q] += g[q] * r[q];
+                        }
+                        for (int q = 0; q < nq; ++q) Ri[q] *= Jac[g0 + q];
+                        int64_t left = 1, right = nq;
+                        for (int k = 0; k < D; ++k) {
+                            right /= tnq[k];
+                            if (act_mode[i] == k + 1) {
+                                mode_apply(D1 + offG[k * (LG + 1) + lk[k]], tnq[k], tnq[k], Ri, X, left, right);
+                                memcpy(Ri, X, sizeof(double) * nq);
+                            }
+                            left *= tnq[k];
+                        }
+                        for (int q = 0; q < nq; ++q) Op[q] += Ri[q];
+                    }
+                    for (int q = 0; q < nq; ++q)                                          /* :1634 */
+                        Op[q] = -0.5 * Op[q] / (Jac[g0 + q] * sq[g0 + q]) + VPsi[(int64_t)ib0 * nq + q];
+                    /* G -> B and weighted scatter */
+                    memcpy(X, Op, sizeof(double) * nq);
+                    double *a = X, *b = Y;
+                    int64_t left = 1, right = nq;
+                    for (int k = 0; k < D; ++k) {
+                        right /= tnq[k];
+                        mode_apply(BTw + offB[k * (LG + 1) + lk[k]], tnb[k], tnq[k], a, b, left, right);
+                        left *= tnb[k];
+                        double *tmp = a; a = b; b = tmp;
+                    }
+                    const double w = W[iG];
+                    for (int j = 0; j < nbT; ++j) {
+                        int32_t m = mp[j];
+                        if (m > 0 && m <= nb) {
+                            double val = w * a[j];
+#pragma omp atomic
+                            y[(int64_t)ib0 * nb + m - 1] += val;
+                        }
+                    }
+                }
+            }
+        }
+        free(X); free(Y); free(Pg); free(VPsi); free(Rj); free(Ri); free(Op);
+    }
+    free(offB); free(offG); free(sum_nq); free(sum_nb);
+    return 0;
+}
+
 int orc_max_threads(void)
 {
 #ifdef _OPENMP

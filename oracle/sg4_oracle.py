@@ -47,6 +47,7 @@ def lib():
         L.orc_n_of_L.restype = C.c_int
         L.orc_n_of_L.argtypes = [C.c_int] * 5
         L.orc_tab_oppsi.restype = C.c_int
+        L.orc_tab_oppsi10.restype = C.c_int
         L.orc_max_threads.restype = C.c_int
         _lib = L
     return _lib
@@ -146,6 +147,33 @@ def tab_oppsi(D, nb_SG, nb0, nb, LG, tab_l, W, tab_nq, tab_nb, mapping, nq_of, n
                          C.c_int(nthreads), C.c_int(iG_begin), C.c_int(iG_end), C.c_int(1 if zero_out else 0))
     if rc != 0:
         raise RuntimeError(f"orc_tab_oppsi failed rc={rc}")
+    return Hpsi
+
+
+def tab_oppsi10(D, nb_SG, nb0, nb, LG, tab_l, W, tab_nq, tab_nb, mapping, nq_of, nb_of, B, BTw, D1,
+                act_mode, V, GG, Jac, sq, psi, nthreads=1, iG_begin=0, iG_end=None):
+    """type_Op=10 action with cached metric tensor (see orc_tab_oppsi10). psi[npsi, nb*nb0]."""
+    L = lib()
+    psi = np.ascontiguousarray(psi, dtype=np.float64)
+    if psi.ndim == 1:
+        psi = psi[None, :]
+    npsi = psi.shape[0]
+    c32 = lambda a: np.ascontiguousarray(a, dtype=np.int32)
+    c64 = lambda a: np.ascontiguousarray(a, dtype=np.float64)
+    tab_l, tab_nq, tab_nb, mapping, nq_of, nb_of, act_mode = map(c32, (tab_l, tab_nq, tab_nb, mapping, nq_of, nb_of, act_mode))
+    W, B, BTw, D1, GG, Jac, sq = map(c64, (W, B, BTw, D1, GG, Jac, sq))
+    Vc = None if V is None else c64(V)
+    Hpsi = np.empty_like(psi)
+    if iG_end is None:
+        iG_end = nb_SG
+    vp = lambda a: C.c_void_p(a.ctypes.data)
+    rc = L.orc_tab_oppsi10(C.c_int(D), C.c_int(nb_SG), C.c_int(nb0), C.c_int64(nb), C.c_int(LG),
+                           vp(tab_l), vp(W), vp(tab_nq), vp(tab_nb), vp(mapping), vp(nq_of), vp(nb_of),
+                           vp(B), vp(BTw), vp(D1), C.c_int(len(act_mode)), vp(act_mode),
+                           C.c_void_p(None) if Vc is None else vp(Vc), vp(GG), vp(Jac), vp(sq),
+                           C.c_int(npsi), vp(psi), vp(Hpsi), C.c_int(nthreads), C.c_int(iG_begin), C.c_int(iG_end), C.c_int(1))
+    if rc != 0:
+        raise RuntimeError(f"orc_tab_oppsi10 failed rc={rc}")
     return Hpsi
 
 

@@ -33,6 +33,17 @@ def oracle_apply(op, psi, nthreads=4, iG_range=None):
                          nthreads=nthreads, iG_begin=lo, iG_end=hi)
 
 
+def oracle_apply10(op, psi, nthreads=4, iG_range=None):
+    """type_Op=10 through oracle/sg4_oracle.c on the inputs of a ParamOp10."""
+    b = op.BasisnD
+    lo, hi = (0, b.nb_SG) if iG_range is None else iG_range
+    return orc.tab_oppsi10(b.D, b.nb_SG, b.nb0, b.nb, b.LG, b.nDind_SmolyakRep_Tab_nDval, b.WeightSG,
+                           b.tab_nq_OF_SRep, b.tab_nb_OF_SRep, b.tab_iB_OF_SRep_TO_iB, b.nq_of, b.nb_of,
+                           b.B, b.BTw, b.D1, op.mode_of_Qact,
+                           None if op.V is None else op.V.ravel(order="F"), op.GG.ravel(order="F"), op.Jac, op.sqRhoOVERJac,
+                           psi, nthreads=nthreads, iG_begin=lo, iG_end=hi)
+
+
 def rel_l2(a, b):
     a = np.asarray(a, dtype=np.float64).ravel()
     b = np.asarray(b, dtype=np.float64).ravel()

@@ -141,3 +141,21 @@ def test_device_entry_point_with_torch(evr):
     op.apply_device_ptr(3, d_psi.data_ptr(), d_out.data_ptr(), torch.cuda.current_stream().cuda_stream)
     torch.cuda.synchronize()
     assert rel_l2(d_out.cpu().numpy(), oracle_apply(op, psi)) < TOL
+
+
+def test_type_op_10_cached_metric(evr):
+    """type_Op=10: d_i J G^ij d_j form with G/Jac/sqrt(rho/J) cached per grid point; HCN shape
+    (3 modes, 10+10L / 1+2L), a 5-mode nq=nb=1+L shape, and two channels."""
+    from helpers import oracle_apply10
+    for basis in (evr.workloads.hm_sg4_basis(3, 4, 5, [10, 1, 1], [10, 2, 2]),
+                  evr.workloads.hm_sg4_basis(5, 2, 4, 1, 1),
+                  evr.workloads.hm_sg4_basis(3, 3, 3, 1, 2, nb0=2)):
+        op = evr.workloads.synthetic_type10(basis)
+        psi = random_psi(basis.nb * basis.nb0, 3, 21)
+        ref = oracle_apply10(op, psi)
+        out = op.apply_host(psi)
+        for i in range(3):
+            assert rel_l2(out[i], ref[i]) < TOL
+    nov = evr.workloads.synthetic_type10(evr.workloads.hm_sg4_basis(3, 3, 3, 1, 2), with_V=False)
+    psi = random_psi(nov.BasisnD.nb, 1, 22)
+    assert rel_l2(nov.apply_host(psi), oracle_apply10(nov, psi)) < TOL

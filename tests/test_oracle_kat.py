@@ -39,3 +39,30 @@ def test_oracle_thread_count_independent(evr):
     a = oracle_apply(op, psi, nthreads=1)
     b = oracle_apply(op, psi, nthreads=4)
     assert np.abs(a - b).max() < 1e-12 * np.abs(a).max()
+
+
+def test_oracle_type10_reduces_to_type1_for_unit_metric(evr):
+    """With G = 1, Jac = 1, rho = 1 the type_Op=10 form is -1/2 sum_i d_i d_i + V: identical to the type_Op=1
+    action in which dnRGG%d2 is replaced by dnRGG%d1 . dnRGG%d1 (the two oracle code paths cross-check)."""
+    from oracle import sg4_oracle as orc
+    b = evr.workloads.hm_sg4_basis(3, 3, 3, 1, 2)
+    rng = np.random.default_rng(0)
+    NQ, n = b.nqq, 3
+    V = rng.standard_normal(NQ)
+    GG = np.zeros((NQ, n, n), order="F")
+    for i in range(n):
+        GG[:, i, i] = 1.0
+    psi = rng.standard_normal((2, b.nb))
+    args = (b.D, b.nb_SG, 1, b.nb, b.LG, b.nDind_SmolyakRep_Tab_nDval, b.WeightSG, b.tab_nq_OF_SRep,
+            b.tab_nb_OF_SRep, b.tab_iB_OF_SRep_TO_iB, b.nq_of, b.nb_of, b.B, b.BTw, b.D1)
+    h10 = orc.tab_oppsi10(*args, [1, 2, 3], V, GG.ravel(order="F"), np.ones(NQ), np.ones(NQ), psi)
+    D1D1 = np.concatenate([(b.tab_basisPrimSG[k][L].D1 @ b.tab_basisPrimSG[k][L].D1).ravel(order="F")
+                           for k in range(b.D) for L in range(b.LG + 1)])
+    ops = evr.workloads.constant_keo_opgrids(3, 1, np.ones(3), V.reshape(-1, 1, 1))
+    tm = np.array(evr.Init_TypeOp(1, 3), dtype=np.int32)
+    gz = [o.grid_zero for o in ops]
+    gc = [o.grid_cte for o in ops]
+    mc = np.array([0.0 if o.Mat_cte is None else o.Mat_cte[0, 0] for o in ops]).reshape(-1, 1)
+    grids = [None if (o.grid_zero or o.grid_cte) else np.asfortranarray(o.Grid).ravel(order="F") for o in ops]
+    h1 = orc.tab_oppsi(*args, D1D1, 1, tm, gz, gc, mc, grids, psi)
+    assert np.abs(h10 - h1).max() < 1e-13 * np.abs(h1).max()
