@@ -23,7 +23,21 @@ from .primitives import hm_primitive
 from .sg4 import Basis_L_TO_n, Init_TypeOp, OpGrid, ParamOp, ParamOp10, SG4Basis, level_sizes
 
 LAMBDA_HH = 0.111803
-EV_TO_AU = 1.0 / 27.211386245988          # CODATA 2018 hartree energy in eV
+
+
+def _au_to_ev_codata2006() -> float:
+    """au -> eV exactly as the reference derives it (default version CODATA2006:
+    Source_PhysicalConstants/sub_module_constant.f90:260-308, constants :788-798):
+    epsi0 = 1/(mhu0 c^2), a0 = (hb/e)^2/me 4 pi epsi0, Eh = e^2/(4 pi epsi0 a0), auTOeV = Eh/e."""
+    c, mhu0, h, e, me = 299792458.0, np.pi * 4e-7, 6.62606896e-34, 1.602176487e-19, 9.10938215e-31
+    epsi0 = 1.0 / (mhu0 * c * c)
+    hb = h / (2.0 * np.pi)
+    a0 = (hb / e) ** 2 / me * 4.0 * np.pi * epsi0
+    Eh = (e * e / a0) / (4.0 * np.pi * epsi0)
+    return Eh / e
+
+
+EV_TO_AU = 1.0 / _au_to_ev_codata2006()   # 1 / 27.2113838656 (ene_unit='eV' of the pyrazine inputs)
 
 
 def hm_sg4_basis(D: int, LB: int, LG: int, A, B, nb0: int = 1, Q0=0.0, scaleQ=1.0) -> SG4Basis:

@@ -159,3 +159,66 @@ def test_type_op_10_cached_metric(evr):
     nov = evr.workloads.synthetic_type10(evr.workloads.hm_sg4_basis(3, 3, 3, 1, 2), with_V=False)
     psi = random_psi(nov.BasisnD.nb, 1, 22)
     assert rel_l2(nov.apply_host(psi), oracle_apply10(nov, psi)) < TOL
+
+
+def test_gpu_pyrazine_autocorrelation_matches_reference(evr, golden):
+    """The H matrix of the 12-D two-state pyrazine model built column by column with the CUDA path (complex
+    psi = two real right-hand sides) reproduces the reference's autocorrelation benchmark (1e-8 tolerance there)."""
+    from test_oracle_kat import _pyrazine_autocorrelation
+    basis, op = evr.workloads.pyrazine_12d(1)
+    n = basis.nb * 2
+    H = op.apply_host(np.eye(n)).T
+    rows = np.array(golden["kat"]["PYR12D_L1_autocor"]["t_re_im_abs"])
+    c = _pyrazine_autocorrelation(H, basis.nb, rows[:, 0])
+    assert max(np.abs(c.real - rows[:, 1]).max(), np.abs(c.imag - rows[:, 2]).max(), np.abs(np.abs(c) - rows[:, 3]).max()) < 1e-10
+
+
+def test_cpp_host_mirror(evr, tmp_path):
+    """The C++ mirror of mod_OpPsi (host/evr_oppsi.hpp: param_psi, param_Op, sub_OpPsi, sub_TabOpPsi) driven by a
+    compiled program over the C-ABI: block of real vectors + complex wave packets, pyrazine two-state model."""
+    import os
+    import struct
+    import subprocess
+    from helpers import flat_op
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = tmp_path / "host_mirror_main"
+    subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++17", os.path.join(root, "tests", "cpp", "host_mirror_main.cpp"),
+                           "-o", str(exe), "-L" + os.path.join(root, "elvibrot-tnumtana_b200"), "-levr_sg4",
+                           "-Wl,-rpath," + os.path.join(root, "elvibrot-tnumtana_b200")])
+    basis, op = evr.workloads.pyrazine_12d(2)
+    b = basis
+    tm, gz, gc, mc, grids = flat_op(op)
+    n = b.nb * b.nb0
+    npsi, ncplx = 3, 2
+    rng = np.random.default_rng(9)
+    psi = rng.standard_normal((npsi, n))
+    cpsi = rng.standard_normal((ncplx, n)) + 1j * rng.standard_normal((ncplx, n))
+
+    def blk(a, dt):
+        a = np.ascontiguousarray(a, dtype=dt)
+        return struct.pack("<q", a.size) + a.tobytes()
+    with open(tmp_path / "in.bin", "wb") as f:
+        f.write(blk([b.D, b.nb_SG, b.nb0, b.nb, b.LG, op.type_Op, op.nb_Term, npsi, ncplx], np.int64))
+        for a, dt in [(b.nDind_SmolyakRep_Tab_nDval, np.int32), (b.WeightSG, np.float64), (b.tab_nq_OF_SRep, np.int32),
+                      (b.tab_nb_OF_SRep, np.int32), (b.tab_iB_OF_SRep_TO_iB, np.int32), (b.nq_of, np.int32), (b.nb_of, np.int32),
+                      (b.B, np.float64), (b.BTw, np.float64), (b.D1, np.float64), (b.D2, np.float64),
+                      (tm, np.int32), (np.array(gz, dtype=np.uint8), np.uint8), (np.array(gc, dtype=np.uint8), np.uint8), (mc, np.float64)]:
+            f.write(blk(a, dt))
+        for g in grids:
+            f.write(blk(np.zeros(0) if g is None else g, np.float64))
+        f.write(blk(psi, np.float64))
+        f.write(blk(np.stack([cpsi.real, cpsi.imag], axis=-1), np.float64))
+    subprocess.check_call([str(exe), str(tmp_path / "in.bin"), str(tmp_path / "out.bin")])
+    raw = open(tmp_path / "out.bin", "rb").read()
+    stops, count = struct.unpack("<qq", raw[:16])
+    assert stops == 2                       # both reference STOP conditions raised
+    assert count == npsi + ncplx            # nb_OpPsi bookkeeping
+    out = np.frombuffer(raw[16:], dtype=np.float64)
+    Hr = out[: npsi * n].reshape(npsi, n)
+    Hc = out[npsi * n:].reshape(ncplx, n, 2)
+    ref_r = oracle_apply(op, psi)
+    ref_c = oracle_apply(op, np.concatenate([cpsi.real, cpsi.imag]))
+    for i in range(npsi):
+        assert rel_l2(Hr[i], ref_r[i]) < TOL
+    for i in range(ncplx):
+        assert rel_l2(Hc[i, :, 0], ref_c[i]) < TOL and rel_l2(Hc[i, :, 1], ref_c[ncplx + i]) < TOL
