@@ -248,22 +248,41 @@ def main():
     e2e = None
     if not args.no_e2e:
         xh, yh = psi_h.numpy(), out_h.numpy()
+
+        def e2e_step():
+            if world == 1:
+                op.apply_host(xh, out=yh)                       # C-ABI evr_sg4_apply: H2D + kernels + D2H
+            else:                                               # replicated psi H2D, term-parallel apply + all-reduce, D2H
+                d_psi.copy_(psi_h, non_blocking=True)
+                tp.apply(d_psi, d_out)
+                out_h.copy_(d_out, non_blocking=True)
+                torch.cuda.current_stream().synchronize()
         for _ in range(2):
-            op.apply_host(xh, out=yh)
+            e2e_step()
         barrier()
         t0 = time.perf_counter()
         for _ in range(args.steps):
-            op.apply_host(xh, out=yh)
-            if world > 1:
-                d_tmp = out_h.cuda(non_blocking=True)
-                dist.all_reduce(d_tmp, op=dist.ReduceOp.SUM)
-                out_h.copy_(d_tmp)
+            e2e_step()
         barrier()
         te = torch.tensor([(time.perf_counter() - t0) / args.steps], dtype=torch.float64, device="cuda")
         if world > 1:
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
         e2e = {"value": 1.0 / float(te[0]), "unit": UNIT, "h2d_bytes_per_step": int(npsi * nvec * 8),
                "d2h_bytes_per_step": int(npsi * nvec * 8)}
+    allreduce_ms = None
+    if world > 1:                                               # the collective alone, for the scaling analysis
+        for _ in range(3):
+            dist.all_reduce(d_out, op=dist.ReduceOp.SUM)
+        barrier()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record(stream)
+        for _ in range(args.steps):
+            dist.all_reduce(d_out, op=dist.ReduceOp.SUM)
+        a1.record(stream)
+        barrier()
+        ta = torch.tensor([a0.elapsed_time(a1) / args.steps], dtype=torch.float64, device="cuda")
+        dist.all_reduce(ta, op=dist.ReduceOp.MAX)
+        allreduce_ms = float(ta[0])
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- roofline of the term kernel (this rank's launch; algorithmic bytes per SURVEY.md 8d)
@@ -295,7 +314,7 @@ def main():
                            "cache": "operator grid + mapping streamed per step (%.0f MB) > L2; no flush needed" % (alg1 / 1e6)
                            if alg1 > 130e6 else "inputs smaller than L2 (L2-warm numbers)",
                            "kernel_path": int(op.info(evr.lib.INFO_PATH)), "setup_s": round(t_setup, 2)},
-                "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks}
+                "e2e": e2e, "allreduce_ms": allreduce_ms, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

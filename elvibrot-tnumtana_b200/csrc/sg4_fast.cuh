@@ -252,11 +252,11 @@ __device__ __forceinline__ void run_pass(const PassArgs &A)
 {
     constexpr int NN1 = N1 * N1, NN2 = N2 * N2, TILE = N1 * N2;
     const int ntiles = A.nq / TILE;
-    const double *B1 = A.pool + A.m1, *W1 = B1 + NN1, *T1 = B1 + 2 * NN1;
-    const double *B2 = A.pool + ((N2 > 1) ? A.m2 : A.m1), *W2 = B2 + NN2, *T2 = B2 + 2 * NN2;
+    const double *__restrict__ B1 = A.pool + A.m1, *__restrict__ W1 = B1 + NN1, *__restrict__ T1 = B1 + 2 * NN1;
+    const double *__restrict__ B2 = A.pool + ((N2 > 1) ? A.m2 : A.m1), *__restrict__ W2 = B2 + NN2, *__restrict__ T2 = B2 + 2 * NN2;
     const int stride = A.stride;
     for (int c = 0; c < A.nb0; ++c) {
-        double *psi = A.psi + c * A.nq, *acc = A.acc + c * A.nq;
+        double *__restrict__ psi = A.psi + c * A.nq, *__restrict__ acc = A.acc + c * A.nq;
         for (int t = A.tid; t < ntiles; t += A.nthr) {
             const int q0 = tile_origin(t, stride, A.magic, TILE);
             double v[N2][N1];
