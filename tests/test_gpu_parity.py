@@ -222,3 +222,42 @@ def test_cpp_host_mirror(evr, tmp_path):
         assert rel_l2(Hr[i], ref_r[i]) < TOL
     for i in range(ncplx):
         assert rel_l2(Hc[i, :, 0], ref_c[i]) < TOL and rel_l2(Hc[i, :, 1], ref_c[ncplx + i]) < TOL
+
+
+def test_fast_path_without_potential_and_with_constant_shift(evr):
+    """Operator forms the fast path must also accept: pure kinetic energy ((0,0) term grid_zero) and a constant
+    (0,0) term (grid_cte, folded into the per-term shift)."""
+    basis = evr.workloads.hm_sg4_basis(6, 3, 3, 1, 2)
+    ops = evr.workloads.constant_keo_opgrids(6, 1, np.linspace(0.5, 1.5, 6), None)
+    op = evr.ParamOp(basis, 1, ops)
+    _check(op, 2)
+    assert op.info(evr.lib.INFO_PATH) == 1
+    ops2 = evr.workloads.constant_keo_opgrids(6, 1, np.ones(6), None)
+    ops2[0] = evr.OpGrid((0, 0), grid_cte=True, Mat_cte=np.array([[0.37]]))
+    op2 = evr.ParamOp(basis, 1, ops2)
+    _check(op2, 1)
+    # first-derivative constant terms (f1) are folded into the same 1-D kinetic matrix
+    ops3 = evr.workloads.constant_keo_opgrids(6, 1, np.ones(6), None)
+    for it, og in enumerate(ops3):
+        if og.derive_termQact[0] > 0 and og.derive_termQact[1] == 0:
+            ops3[it] = evr.OpGrid(og.derive_termQact, grid_cte=True, Mat_cte=np.array([[0.1 * og.derive_termQact[0]]]))
+    op3 = evr.ParamOp(basis, 1, ops3)
+    _check(op3, 1)
+    assert op3.info(evr.lib.INFO_PATH) == 1
+    # a constant MIXED derivative term does not qualify: generic kernel
+    ops4 = evr.workloads.constant_keo_opgrids(6, 1, np.ones(6), None)
+    for it, og in enumerate(ops4):
+        if og.derive_termQact == (1, 2):
+            ops4[it] = evr.OpGrid((1, 2), grid_cte=True, Mat_cte=np.array([[-0.2]]))
+    op4 = evr.ParamOp(basis, 1, ops4)
+    _check(op4, 1)
+    assert op4.info(evr.lib.INFO_PATH) == 0
+
+
+def test_empty_term_range_and_single_term(evr):
+    basis, op = evr.workloads.henon_heiles(4, 2)
+    psi = random_psi(basis.nb, 1, 3)
+    empty = evr.ParamOp(basis, 1, op.OpGrid, iG_range=(5, 5))
+    assert np.abs(empty.apply_host(psi)).max() == 0.0
+    one = evr.ParamOp(basis, 1, op.OpGrid, iG_range=(7, 8))
+    assert rel_l2(one.apply_host(psi), oracle_apply(op, psi, iG_range=(7, 8))) < TOL
