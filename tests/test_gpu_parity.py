@@ -1,6 +1,7 @@
 """Parity of the CUDA path (through the C-ABI) against the CPU oracle.  Tolerance: relative L2
 <= 1e-12 per right-hand side (north star), eigenvalues <= 1e-6 cm^-1 = 4.6e-12 au against the oracle."""
 import ctypes as C
+import os
 
 import numpy as np
 import pytest
@@ -229,9 +230,11 @@ def test_fast_path_without_potential_and_with_constant_shift(evr):
     (0,0) term (grid_cte, folded into the per-term shift)."""
     basis = evr.workloads.hm_sg4_basis(6, 3, 3, 1, 2)
     ops = evr.workloads.constant_keo_opgrids(6, 1, np.linspace(0.5, 1.5, 6), None)
+    # which kernel is selected is only asserted when the selection is not overridden from the environment
+    fast = 0 if os.environ.get("EVR_SG4_FORCE_GENERIC") == "1" else 1
     op = evr.ParamOp(basis, 1, ops)
     _check(op, 2)
-    assert op.info(evr.lib.INFO_PATH) == 1
+    assert op.info(evr.lib.INFO_PATH) == fast
     ops2 = evr.workloads.constant_keo_opgrids(6, 1, np.ones(6), None)
     ops2[0] = evr.OpGrid((0, 0), grid_cte=True, Mat_cte=np.array([[0.37]]))
     op2 = evr.ParamOp(basis, 1, ops2)
@@ -243,7 +246,7 @@ def test_fast_path_without_potential_and_with_constant_shift(evr):
             ops3[it] = evr.OpGrid(og.derive_termQact, grid_cte=True, Mat_cte=np.array([[0.1 * og.derive_termQact[0]]]))
     op3 = evr.ParamOp(basis, 1, ops3)
     _check(op3, 1)
-    assert op3.info(evr.lib.INFO_PATH) == 1
+    assert op3.info(evr.lib.INFO_PATH) == fast
     # a constant MIXED derivative term does not qualify: generic kernel
     ops4 = evr.workloads.constant_keo_opgrids(6, 1, np.ones(6), None)
     for it, og in enumerate(ops4):
