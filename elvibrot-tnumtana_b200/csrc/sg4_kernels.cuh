@@ -27,6 +27,13 @@ struct TermDev {                 // one per Smolyak term of this plan's range (w
     int       nbT, nq;           // prod nb_k, prod nq_k
     int       lev_off;           // start of the term's D levels in d_lev
     int       pad;
+    double    wfold;             // weight * prod over the 1x1 modes of B*BTw (generic kernel skips those modes)
+};
+
+struct GenClassDev {             // one launch of the generic kernel: terms of similar size, one CTA size
+    int term_begin, n_terms;     // range in work order
+    int cap;                     // doubles per shared-memory buffer (max term size of the class * nb0)
+    int pad;
 };
 
 struct OpTermDev {               // one per live (not grid_zero) operator term
@@ -76,15 +83,17 @@ __device__ __forceinline__ void mode_product(const double *__restrict__ M, int n
 }
 
 // ---- generic term kernel (any type_Op 0/1 term list, any mode sizes that fit) ----------
+// Launched once per size class (GenClassDev) with a CTA of 32/64/128/256 threads, so that the many small
+// terms of a curvilinear configuration (HNO3_UT: 38 points per term on average) do not idle a wide CTA.
 // dynamic smem: [2*cap doubles][ints: nq_of,nb_of,offB,offG (4*D*(LG+1))][per-term ints 5*D]
 __global__ void __launch_bounds__(256)
-sg4_term_kernel_generic(const PlanDev P, const int npsi,
+sg4_term_kernel_generic(const PlanDev P, const GenClassDev Cc, const int npsi,
                         const double *__restrict__ psi, double *__restrict__ Hpsi)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double *bufA = reinterpret_cast<double *>(smem_raw);
-    double *bufB = bufA + P.cap;
-    int *s_nq_of = reinterpret_cast<int *>(bufB + P.cap);
+    double *bufB = bufA + Cc.cap;
+    int *s_nq_of = reinterpret_cast<int *>(bufB + Cc.cap);
     const int nT = P.D * (P.LG + 1);
     int *s_nb_of = s_nq_of + nT;
     int *s_offB  = s_nb_of + nT;
@@ -106,21 +115,20 @@ sg4_term_kernel_generic(const PlanDev P, const int npsi,
 
     // work item = (term, right-hand side): blocks of RHS (Davidson) fill the GPU even when a configuration has
     // few Smolyak terms (HCN_UT: 85 terms x 27 vectors)
-    const long long n_items = (long long)P.n_terms * npsi;
+    const long long n_items = (long long)Cc.n_terms * npsi;
     for (long long w = blockIdx.x; w < n_items; w += gridDim.x) {
         const int it = (int)(w / npsi);
         const int ip_only = (int)(w - (long long)it * npsi);
-        const TermDev T = P.terms[it];
+        const TermDev T = P.terms[Cc.term_begin + it];
         const uint8_t *lev = P.lev + T.lev_off;
         __syncthreads();               // previous term fully done before the per-term tables change
-        if (threadIdx.x == 0) {
-            int str = 1;
-            for (int k = 0; k < D; ++k) {
-                const int i = k * (P.LG + 1) + lev[k];
-                s_tnq[k] = s_nq_of[i]; s_tnb[k] = s_nb_of[i];
-                s_oB[k] = s_offB[i];   s_oG[k] = s_offG[i];
-                s_str[k] = str; str *= s_nq_of[i];
-            }
+        for (int k = threadIdx.x; k < D; k += blockDim.x) {
+            const int i = k * (P.LG + 1) + lev[k];
+            s_tnq[k] = s_nq_of[i]; s_tnb[k] = s_nb_of[i];
+            s_oB[k] = s_offB[i];   s_oG[k] = s_offG[i];
+            int str = 1;               // grid stride of mode k (first mode fastest)
+            for (int j = 0; j < k; ++j) str *= s_nq_of[j * (P.LG + 1) + lev[j]];
+            s_str[k] = str;
         }
         __syncthreads();
         const int nq = T.nq, nbT = T.nbT;
@@ -143,14 +151,9 @@ sg4_term_kernel_generic(const PlanDev P, const int npsi,
                 for (int k = 0; k < D; ++k) {
                     const int nbk = s_tnb[k], nqk = s_tnq[k];
                     right /= nbk;
-                    if (nbk == 1 && nqk == 1) {
-                        const double s = __ldg(P.B + s_oB[k]);
-                        const int total = left * right;
-                        for (int o = threadIdx.x; o < total; o += blockDim.x) cur[o] *= s;
-                    } else {
-                        mode_product(P.B + s_oB[k], nqk, nbk, cur, oth, left, right);
-                        double *t = cur; cur = oth; oth = t;
-                    }
+                    if (nbk == 1 && nqk == 1) continue;        // scalar folded into T.wfold by the plan
+                    mode_product(P.B + s_oB[k], nqk, nbk, cur, oth, left, right);
+                    double *t = cur; cur = oth; oth = t;
                     left *= nqk;
                     __syncthreads();
                 }
@@ -222,14 +225,9 @@ sg4_term_kernel_generic(const PlanDev P, const int npsi,
                 for (int k = 0; k < D; ++k) {
                     const int nbk = s_tnb[k], nqk = s_tnq[k];
                     right /= nqk;
-                    if (nbk == 1 && nqk == 1) {
-                        const double s = __ldg(P.BTw + s_oB[k]);
-                        const int total = left * right;
-                        for (int o = threadIdx.x; o < total; o += blockDim.x) cur[o] *= s;
-                    } else {
-                        mode_product(P.BTw + s_oB[k], nbk, nqk, cur, oth, left, right);
-                        double *t = cur; cur = oth; oth = t;
-                    }
+                    if (nbk == 1 && nqk == 1) continue;
+                    mode_product(P.BTw + s_oB[k], nbk, nqk, cur, oth, left, right);
+                    double *t = cur; cur = oth; oth = t;
                     left *= nbk;
                     __syncthreads();
                 }
@@ -239,7 +237,7 @@ sg4_term_kernel_generic(const PlanDev P, const int npsi,
                 const int m = mp[j];
                 if (m > 0)
                     for (int c = 0; c < nb0; ++c)
-                        atomicAdd(y + (long long)c * P.nb + (m - 1), T.weight * cur[c * nbT + j]);
+                        atomicAdd(y + (long long)c * P.nb + (m - 1), T.wfold * cur[c * nbT + j]);
             }
             __syncthreads();
         }

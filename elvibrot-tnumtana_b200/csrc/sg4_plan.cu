@@ -94,6 +94,11 @@ struct evr_sg4_plan {
     cudaEvent_t ev_fork = nullptr, ev_join[9] = {nullptr};
     size_t smem_bytes = 0;
     int grid_ctas = 0, gen_ctas_max = 0;
+    // generic kernel: one launch per term-size class (CTA of 256/128/64/32 threads)
+    int n_gclasses = 0;
+    evr::GenClassDev gclass[4];
+    int gclass_threads[4] = {0}, gclass_occ[4] = {0};
+    size_t gclass_smem[4] = {0};
     evr::PlanDev pd{};
 };
 
@@ -176,23 +181,27 @@ extern "C" int evr_sg4_plan_create(evr_sg4_plan **out, int device,
     }
 
     // per-term cost, capacity, work order
-    std::vector<double> cost(p->n_terms);
+    std::vector<double> cost(p->n_terms), wfold(p->n_terms);
+    std::vector<int64_t> tsize(p->n_terms);
     int64_t cap = 1, flops = 0;
     for (int t = 0; t < p->n_terms; ++t) {
         const int iG = iG_begin + t;
         int64_t mx = 1, sumn = 0;
+        double fold = WeightSG[iG];
         int64_t left = 1, right = tab_nb[iG];
         for (int k = 0; k < D; ++k) {
             int l = tab_l[(size_t)iG * D + k];
             int a = nq_of[k * (LG + 1) + l], b = nb_of[k * (LG + 1) + l];
             mx *= std::max(a, b);
             sumn += a + b;
+            if (a == 1 && b == 1) fold *= B[offB[k * (LG + 1) + l]] * BTw[offB[k * (LG + 1) + l]];
             right /= b;
             flops += 2 * 2 * left * a * b * right;       // B->G and G->B (same count)
             left *= a;
         }
         cap = std::max(cap, mx);
         cost[t] = (double)tab_nq[iG] * (double)sumn;
+        wfold[t] = fold; tsize[t] = mx;
     }
     p->flops_npsi1 = flops * nb0;
     if (cap * nb0 * 2 * (int64_t)sizeof(double) > 220 * 1024) {
@@ -214,7 +223,12 @@ extern "C" int evr_sg4_plan_create(evr_sg4_plan **out, int device,
     p->h_cost = cost;
     p->order.resize(p->n_terms);
     std::iota(p->order.begin(), p->order.end(), 0);
-    std::stable_sort(p->order.begin(), p->order.end(), [&](int a, int b) { return cost[a] > cost[b]; });
+    // size classes of the generic kernel (CTA threads 256 / 128 / 64 / 32), then cost descending inside a class
+    auto gclass_of = [&](int t) { return tsize[t] > 768 ? 0 : (tsize[t] > 192 ? 1 : (tsize[t] > 48 ? 2 : 3)); };
+    std::stable_sort(p->order.begin(), p->order.end(), [&](int a, int b) {
+        const int ca = gclass_of(a), cb = gclass_of(b);
+        return ca != cb ? ca < cb : cost[a] > cost[b];
+    });
 
     std::vector<evr::TermDev> terms(p->n_terms);
     std::vector<uint8_t> lev((size_t)p->n_terms * D);
@@ -225,7 +239,7 @@ extern "C" int evr_sg4_plan_create(evr_sg4_plan **out, int device,
         T.grid_off = pre_nq[iG] - p->grid_start;
         T.weight = WeightSG[iG];
         T.nbT = tab_nb[iG]; T.nq = tab_nq[iG];
-        T.lev_off = w * D; T.pad = 0;
+        T.lev_off = w * D; T.pad = 0; T.wfold = wfold[t];
         for (int k = 0; k < D; ++k) lev[(size_t)w * D + k] = (uint8_t)tab_l[(size_t)iG * D + k];
     }
     int rc = 0;
@@ -257,12 +271,28 @@ extern "C" int evr_sg4_plan_create(evr_sg4_plan **out, int device,
     if (cudaFuncSetAttribute(evr::sg4_term_kernel_generic, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_bytes) != cudaSuccess) {
         evr_sg4_plan_destroy(&p); return fail("evr_sg4_plan_create: cudaFuncSetAttribute(smem) failed");
     }
-    int occ = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, evr::sg4_term_kernel_generic, 256, p->smem_bytes) != cudaSuccess || occ < 1) {
-        evr_sg4_plan_destroy(&p); return fail("evr_sg4_plan_create: kernel cannot be resident (occupancy 0)");
+    {
+        static const int class_threads[4] = {256, 128, 64, 32};
+        int w0 = 0;
+        for (int c = 0; c < 4; ++c) {
+            int w1 = w0;
+            int64_t ccap = 1;
+            while (w1 < p->n_terms && gclass_of(p->order[w1]) == c) { ccap = std::max(ccap, tsize[p->order[w1]] * nb0); ++w1; }
+            if (w1 == w0) continue;
+            const int g = p->n_gclasses++;
+            p->gclass[g].term_begin = w0; p->gclass[g].n_terms = w1 - w0; p->gclass[g].cap = (int)ccap; p->gclass[g].pad = 0;
+            p->gclass_threads[g] = class_threads[c];
+            p->gclass_smem[g] = (size_t)2 * ccap * sizeof(double) + (size_t)(4 * nT + 5 * D) * sizeof(int);
+            int occ = 0;
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, evr::sg4_term_kernel_generic, class_threads[c], p->gclass_smem[g]) != cudaSuccess || occ < 1) {
+                evr_sg4_plan_destroy(&p); return fail("evr_sg4_plan_create: kernel cannot be resident (occupancy 0)");
+            }
+            p->gclass_occ[g] = occ;
+            w0 = w1;
+        }
+        p->gen_ctas_max = p->n_gclasses ? p->sm_count * p->gclass_occ[0] : p->sm_count;
+        p->grid_ctas = p->n_gclasses ? std::max(1, std::min(p->gclass[0].n_terms, p->gen_ctas_max)) : 1;
     }
-    p->grid_ctas = std::max(1, std::min(p->n_terms, p->sm_count * occ));
-    p->gen_ctas_max = p->sm_count * occ;
 
     evr::PlanDev &pd = p->pd;
     pd.D = D; pd.LG = LG; pd.nb0 = nb0; pd.n_terms = p->n_terms; pd.nb = nb; pd.NQ_local = p->NQ_local;
@@ -764,10 +794,20 @@ static int launch(evr_sg4_plan *p, int npsi, const double *d_psi_user, double *d
             evr::sg4_term_kernel_type10<<<ctas, 256, p->smem10, st>>>(p->pd, p->o10, npsi, d_psi, d_Hpsi);
             p->launches += 1;
         } else {
-            const long long items = (long long)p->n_terms * npsi;
-            const int ctas = (int)std::max<long long>(1, std::min<long long>(items, (long long)p->gen_ctas_max));
-            evr::sg4_term_kernel_generic<<<ctas, 256, p->smem_bytes, st>>>(p->pd, npsi, d_psi, d_Hpsi);
-            p->launches += 1;
+            const bool multi = p->n_gclasses > 1 && p->ev_fork != nullptr;
+            if (multi) CUDA_TRY(cudaEventRecord(p->ev_fork, st));
+            for (int c = 0; c < p->n_gclasses; ++c) {
+                cudaStream_t sc = (multi && c > 0) ? p->side[c] : st;
+                if (multi && c > 0) CUDA_TRY(cudaStreamWaitEvent(sc, p->ev_fork, 0));
+                const long long items = (long long)p->gclass[c].n_terms * npsi;
+                const int ctas = (int)std::max<long long>(1, std::min<long long>(items, (long long)p->sm_count * p->gclass_occ[c]));
+                evr::sg4_term_kernel_generic<<<ctas, p->gclass_threads[c], p->gclass_smem[c], sc>>>(p->pd, p->gclass[c], npsi, d_psi, d_Hpsi);
+                p->launches += 1;
+                if (multi && c > 0) {
+                    CUDA_TRY(cudaEventRecord(p->ev_join[c], sc));
+                    CUDA_TRY(cudaStreamWaitEvent(st, p->ev_join[c], 0));
+                }
+            }
         }
         CUDA_TRY(cudaGetLastError());
     }
