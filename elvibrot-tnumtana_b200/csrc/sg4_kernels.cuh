@@ -33,7 +33,7 @@ struct TermDev {                 // one per Smolyak term of this plan's range (w
 struct GenClassDev {             // one launch of the generic kernel: terms of similar size, one CTA size
     int term_begin, n_terms;     // range in work order
     int cap;                     // doubles per shared-memory buffer (max term size of the class * nb0)
-    int pad;
+    int dcache;                  // 1: third buffer holds the first derivative of the current sweep mode
 };
 
 struct OpTermDev {               // one per live (not grid_zero) operator term
@@ -58,22 +58,33 @@ struct PlanDev {
     const int32_t   *offB;       // [D*(LG+1)] offsets into B/BTw pools
     const int32_t   *offG;       // [D*(LG+1)] offsets into D1/D2 pools
     const double    *B, *BTw, *D1, *D2;
-    const OpTermDev *opterms;    // [n_opterms]
+    const OpTermDev *opterms;    // [n_opterms]: n_plain on-the-fly terms, then the terms of each sweep
     const double    *grids;      // [n_var][nb0*nb0][NQ_local]  (slot-major; (i + nb0*j)-major; point)
+    // mixed-derivative sweeps: sweep s caches d/dQ_a psi (a = sweep_mode[s]) of the whole term in shared memory
+    // and serves opterms [sweep_begin[s], sweep_begin[s+1]): d_a d_b (m1 = a, m2 = b) and d_a alone (m2 = -1)
+    int n_plain, n_sweeps;
+    int sweep_mode[EVR_MAXD];
+    int sweep_begin[EVR_MAXD + 1];
 };
+
+// ---- division by a per-term constant: q / d = umulhi(q, magic(d)) --------------------------------
+// magic(d) = floor(2^32 / d) + 1, exact while q * d < 2^32 (term sizes are < 2^15 values); d = 1 is encoded as 0
+__device__ __forceinline__ unsigned magic_of(const int d) { return d <= 1 ? 0u : 0xFFFFFFFFu / (unsigned)d + 1u; }
+__device__ __forceinline__ int mdiv(const int q, const unsigned mg) { return mg ? (int)__umulhi((unsigned)q, mg) : q; }
 
 // ---- generic one-mode product through shared memory ----------------------------------
 //   out[a + left*(q + n_out*c)] = sum_b M[q + n_out*b] * in[a + left*(b + n_in*c)]
 //   a < left, c < right (right already includes the channel count), M in global (L1-resident).
 __device__ __forceinline__ void mode_product(const double *__restrict__ M, int n_out, int n_in,
-                                             const double *in, double *out, int left, int right)
+                                             const double *in, double *out, int left, int right,
+                                             const unsigned mg_left, const unsigned mg_lo)
 {
     const int total = left * n_out * right;
     const int lo = left * n_out;
     for (int o = threadIdx.x; o < total; o += blockDim.x) {
-        const int c = o / lo;
+        const int c = mdiv(o, mg_lo);
         const int r = o - c * lo;
-        const int q = r / left;
+        const int q = mdiv(r, mg_left);
         const int a = r - q * left;
         const double *x = in + a + left * n_in * c;
         double s = 0.0;
@@ -85,15 +96,18 @@ __device__ __forceinline__ void mode_product(const double *__restrict__ M, int n
 // ---- generic term kernel (any type_Op 0/1 term list, any mode sizes that fit) ----------
 // Launched once per size class (GenClassDev) with a CTA of 32/64/128/256 threads, so that the many small
 // terms of a curvilinear configuration (HNO3_UT: 38 points per term on average) do not idle a wide CTA.
-// dynamic smem: [2*cap doubles][ints: nq_of,nb_of,offB,offG (4*D*(LG+1))][per-term ints 5*D]
-__global__ void __launch_bounds__(256)
+// dynamic smem: [2 or 3 * cap doubles][ints: nq_of,nb_of,offB,offG (4*D*(LG+1))][per-term ints 5*D + 3*(D+1)]
+//               [3 ints per operator term]
+#define EVR_GEN_SMEM_INTS(nT, D, nop) (4 * (nT) + 5 * (D) + 3 * ((D) + 1) + 3 * (nop))
+__global__ void __launch_bounds__(256, 4)
 sg4_term_kernel_generic(const PlanDev P, const GenClassDev Cc, const int npsi,
                         const double *__restrict__ psi, double *__restrict__ Hpsi)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double *bufA = reinterpret_cast<double *>(smem_raw);
     double *bufB = bufA + Cc.cap;
-    int *s_nq_of = reinterpret_cast<int *>(bufB + Cc.cap);
+    double *bufC = bufB + Cc.cap;                  // only with Cc.dcache
+    int *s_nq_of = reinterpret_cast<int *>(bufB + (Cc.dcache ? 2 : 1) * Cc.cap);
     const int nT = P.D * (P.LG + 1);
     int *s_nb_of = s_nq_of + nT;
     int *s_offB  = s_nb_of + nT;
@@ -103,10 +117,17 @@ sg4_term_kernel_generic(const PlanDev P, const GenClassDev Cc, const int npsi,
     int *s_oB    = s_tnb + P.D;        //           table offsets for (k,l_k)
     int *s_oG    = s_oB + P.D;
     int *s_str   = s_oG + P.D;         //           grid stride of mode k (first mode fastest)
+    unsigned *s_mgq = reinterpret_cast<unsigned *>(s_str + P.D);   // magic of prod_{j<k} nq_j, k = 0..D
+    unsigned *s_mgb = s_mgq + P.D + 1;                             // magic of prod_{j<k} nb_j, k = 0..D
+    unsigned *s_mgn = s_mgb + P.D + 1;                             // magic of nq_k
+    int *s_op = reinterpret_cast<int *>(s_mgn + P.D + 1);          // per operator term: m1, m2, grid_slot
 
     for (int i = threadIdx.x; i < nT; i += blockDim.x) {
         s_nq_of[i] = P.nq_of[i]; s_nb_of[i] = P.nb_of[i];
         s_offB[i] = P.offB[i];   s_offG[i] = P.offG[i];
+    }
+    for (int t = threadIdx.x; t < P.n_opterms; t += blockDim.x) {
+        s_op[3 * t] = P.opterms[t].m1; s_op[3 * t + 1] = P.opterms[t].m2; s_op[3 * t + 2] = P.opterms[t].grid_slot;
     }
     __syncthreads();
 
@@ -122,13 +143,27 @@ sg4_term_kernel_generic(const PlanDev P, const GenClassDev Cc, const int npsi,
         const TermDev T = P.terms[Cc.term_begin + it];
         const uint8_t *lev = P.lev + T.lev_off;
         __syncthreads();               // previous term fully done before the per-term tables change
-        for (int k = threadIdx.x; k < D; k += blockDim.x) {
-            const int i = k * (P.LG + 1) + lev[k];
-            s_tnq[k] = s_nq_of[i]; s_tnb[k] = s_nb_of[i];
-            s_oB[k] = s_offB[i];   s_oG[k] = s_offG[i];
-            int str = 1;               // grid stride of mode k (first mode fastest)
-            for (int j = 0; j < k; ++j) str *= s_nq_of[j * (P.LG + 1) + lev[j]];
-            s_str[k] = str;
+        for (int k = threadIdx.x; k <= D; k += blockDim.x) {
+            int strq = 1, strb = 1;    // grid / basis stride of mode k (first mode fastest)
+            for (int j = 0; j < k; ++j) { strq *= s_nq_of[j * (P.LG + 1) + lev[j]]; strb *= s_nb_of[j * (P.LG + 1) + lev[j]]; }
+            s_mgq[k] = magic_of(strq); s_mgb[k] = magic_of(strb);
+            if (k < D) {
+                const int i = k * (P.LG + 1) + lev[k];
+                s_tnq[k] = s_nq_of[i]; s_tnb[k] = s_nb_of[i];
+                s_oB[k] = s_offB[i];   s_oG[k] = s_offG[i];
+                s_str[k] = strq;       s_mgn[k] = magic_of(s_nq_of[i]);
+            }
+        }
+        // pull the term's slices of the operator grids into L2 while the gather and the B->G passes run
+        if (P.n_var > 0) {
+            const int lines = (T.nq * 8 + 127) / 128 + 1;
+            const int nslice = P.n_var * nb0 * nb0;
+            const char *g0 = reinterpret_cast<const char *>(P.grids + T.grid_off);
+            for (int i = threadIdx.x; i < nslice * lines; i += blockDim.x) {
+                const int sl = i / lines, ln = i - sl * lines;
+                const int byte = min(ln * 128, T.nq * 8 - 8);
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(g0 + (long long)sl * P.NQ_local * 8 + byte));
+            }
         }
         __syncthreads();
         const int nq = T.nq, nbT = T.nbT;
@@ -152,21 +187,39 @@ sg4_term_kernel_generic(const PlanDev P, const GenClassDev Cc, const int npsi,
                     const int nbk = s_tnb[k], nqk = s_tnq[k];
                     right /= nbk;
                     if (nbk == 1 && nqk == 1) continue;        // scalar folded into T.wfold by the plan
-                    mode_product(P.B + s_oB[k], nqk, nbk, cur, oth, left, right);
+                    mode_product(P.B + s_oB[k], nqk, nbk, cur, oth, left, right, s_mgq[k], s_mgq[k + 1]);
                     double *t = cur; cur = oth; oth = t;
                     left *= nqk;
                     __syncthreads();
                 }
             }
             // ---- operator on the term grid: oth(q,i) = sum_iterm sum_j F(q,i,j) [d psi](q,j)
+            auto add_term = [&](const int t, const double (&d)[EVR_MAXCH], double (&acc)[EVR_MAXCH], const int q) {
+                const int slot = s_op[3 * t + 2];
+                if (slot < 0) {
+                    const double *cte = P.opterms[t].cte;
+#pragma unroll
+                    for (int i = 0; i < EVR_MAXCH; ++i) if (i < nb0)
+#pragma unroll
+                        for (int j = 0; j < EVR_MAXCH; ++j) if (j < nb0)
+                            acc[i] = fma(__ldg(cte + i + nb0 * j), d[j], acc[i]);
+                } else {
+                    const double *g = P.grids + ((long long)slot * nb0 * nb0) * P.NQ_local + T.grid_off + q;
+#pragma unroll
+                    for (int i = 0; i < EVR_MAXCH; ++i) if (i < nb0)
+#pragma unroll
+                        for (int j = 0; j < EVR_MAXCH; ++j) if (j < nb0)
+                            acc[i] = fma(__ldg(g + (long long)(i + nb0 * j) * P.NQ_local), d[j], acc[i]);
+                }
+            };
+            const int n_otf = Cc.dcache ? P.n_plain : P.n_opterms;    // terms whose derivative is formed on the fly
             for (int q = threadIdx.x; q < nq; q += blockDim.x) {
                 double acc[EVR_MAXCH];
 #pragma unroll
                 for (int i = 0; i < EVR_MAXCH; ++i) acc[i] = 0.0;
-                for (int t = 0; t < P.n_opterms; ++t) {
-                    const OpTermDev &O = P.opterms[t];
+                for (int t = 0; t < n_otf; ++t) {
                     double d[EVR_MAXCH];
-                    const int m1 = O.m1, m2 = O.m2;
+                    const int m1 = s_op[3 * t], m2 = s_op[3 * t + 1];
                     if (m1 < 0 && m2 < 0) {
 #pragma unroll
                         for (int j = 0; j < EVR_MAXCH; ++j) if (j < nb0) d[j] = cur[j * nq + q];
@@ -174,7 +227,8 @@ sg4_term_kernel_generic(const PlanDev P, const GenClassDev Cc, const int npsi,
                         const int k = (m1 >= 0) ? m1 : m2;
                         const double *M = ((m1 == m2) ? P.D2 : P.D1) + s_oG[k];
                         const int n = s_tnq[k], st = s_str[k];
-                        const int qk = (q / st) % n;
+                        const int qd = mdiv(q, s_mgq[k]);
+                        const int qk = qd - mdiv(qd, s_mgn[k]) * n;
                         const int base = q - qk * st;
 #pragma unroll
                         for (int j = 0; j < EVR_MAXCH; ++j) if (j < nb0) {
@@ -185,7 +239,8 @@ sg4_term_kernel_generic(const PlanDev P, const GenClassDev Cc, const int npsi,
                     } else {
                         const double *Ma = P.D1 + s_oG[m1], *Mb = P.D1 + s_oG[m2];
                         const int na = s_tnq[m1], sa = s_str[m1], nbb = s_tnq[m2], sb = s_str[m2];
-                        const int qa = (q / sa) % na, qb = (q / sb) % nbb;
+                        const int qda = mdiv(q, s_mgq[m1]), qdb = mdiv(q, s_mgq[m2]);
+                        const int qa = qda - mdiv(qda, s_mgn[m1]) * na, qb = qdb - mdiv(qdb, s_mgn[m2]) * nbb;
                         const int base = q - qa * sa - qb * sb;
 #pragma unroll
                         for (int j = 0; j < EVR_MAXCH; ++j) if (j < nb0) {
@@ -199,25 +254,62 @@ sg4_term_kernel_generic(const PlanDev P, const GenClassDev Cc, const int npsi,
                             d[j] = s;
                         }
                     }
-                    if (O.grid_slot < 0) {
-#pragma unroll
-                        for (int i = 0; i < EVR_MAXCH; ++i) if (i < nb0)
-#pragma unroll
-                            for (int j = 0; j < EVR_MAXCH; ++j) if (j < nb0)
-                                acc[i] = fma(O.cte[i + nb0 * j], d[j], acc[i]);
-                    } else {
-                        const double *g = P.grids + ((long long)O.grid_slot * nb0 * nb0) * P.NQ_local + T.grid_off + q;
-#pragma unroll
-                        for (int i = 0; i < EVR_MAXCH; ++i) if (i < nb0)
-#pragma unroll
-                            for (int j = 0; j < EVR_MAXCH; ++j) if (j < nb0)
-                                acc[i] = fma(__ldg(g + (long long)(i + nb0 * j) * P.NQ_local), d[j], acc[i]);
-                    }
+                    add_term(t, d, acc, q);
                 }
 #pragma unroll
                 for (int i = 0; i < EVR_MAXCH; ++i) if (i < nb0) oth[i * nq + q] = acc[i];
             }
             __syncthreads();
+            if (Cc.dcache) {
+                // mixed derivatives d_a d_b: the first derivative along a is formed once per sweep for the whole
+                // term (n_a multiply-adds per point) and every term of the sweep needs n_b more, instead of
+                // n_a*n_b per point and term on the fly
+                for (int sw = 0; sw < P.n_sweeps; ++sw) {
+                    const int a = P.sweep_mode[sw];
+                    const int na = s_tnq[a], sa = s_str[a];
+                    const double *Ma = P.D1 + s_oG[a];
+                    for (int o = threadIdx.x; o < nq * nb0; o += blockDim.x) {
+                        const int j = mdiv(o, s_mgq[D]), q = o - j * nq;
+                        const int qda = mdiv(q, s_mgq[a]);
+                        const int qa = qda - mdiv(qda, s_mgn[a]) * na;
+                        const double *x = cur + j * nq + (q - qa * sa);
+                        double g = 0.0;
+                        for (int b = 0; b < na; ++b) g = fma(__ldg(Ma + qa + na * b), x[b * sa], g);
+                        bufC[o] = g;
+                    }
+                    __syncthreads();
+                    const int t0 = P.sweep_begin[sw], t1 = P.sweep_begin[sw + 1];
+                    for (int q = threadIdx.x; q < nq; q += blockDim.x) {
+                        double acc[EVR_MAXCH];
+#pragma unroll
+                        for (int i = 0; i < EVR_MAXCH; ++i) acc[i] = (i < nb0) ? oth[i * nq + q] : 0.0;
+                        for (int t = t0; t < t1; ++t) {
+                            double d[EVR_MAXCH];
+                            const int m2 = s_op[3 * t + 1];
+                            if (m2 < 0) {
+#pragma unroll
+                                for (int j = 0; j < EVR_MAXCH; ++j) if (j < nb0) d[j] = bufC[j * nq + q];
+                            } else {
+                                const double *Mb = P.D1 + s_oG[m2];
+                                const int nbb = s_tnq[m2], sb = s_str[m2];
+                                const int qdb = mdiv(q, s_mgq[m2]);
+                                const int qb = qdb - mdiv(qdb, s_mgn[m2]) * nbb;
+                                const int base = q - qb * sb;
+#pragma unroll
+                                for (int j = 0; j < EVR_MAXCH; ++j) if (j < nb0) {
+                                    double s = 0.0;
+                                    for (int b2 = 0; b2 < nbb; ++b2) s = fma(__ldg(Mb + qb + nbb * b2), bufC[j * nq + base + b2 * sb], s);
+                                    d[j] = s;
+                                }
+                            }
+                            add_term(t, d, acc, q);
+                        }
+#pragma unroll
+                        for (int i = 0; i < EVR_MAXCH; ++i) if (i < nb0) oth[i * nq + q] = acc[i];
+                    }
+                    __syncthreads();
+                }
+            }
             { double *t = cur; cur = oth; oth = t; }
             // ---- G -> B
             {
@@ -226,7 +318,7 @@ sg4_term_kernel_generic(const PlanDev P, const GenClassDev Cc, const int npsi,
                     const int nbk = s_tnb[k], nqk = s_tnq[k];
                     right /= nqk;
                     if (nbk == 1 && nqk == 1) continue;
-                    mode_product(P.BTw + s_oB[k], nbk, nqk, cur, oth, left, right);
+                    mode_product(P.BTw + s_oB[k], nbk, nqk, cur, oth, left, right, s_mgb[k], s_mgb[k + 1]);
                     double *t = cur; cur = oth; oth = t;
                     left *= nbk;
                     __syncthreads();
@@ -331,7 +423,7 @@ sg4_term_kernel_type10(const PlanDev P, const Op10Dev O, const int npsi,
                     const int total = left * right;
                     for (int o = threadIdx.x; o < total; o += blockDim.x) cur[o] *= s;
                 } else {
-                    mode_product(P.B + s_oB[k], nqk, nbk, cur, oth, left, right);
+                    mode_product(P.B + s_oB[k], nqk, nbk, cur, oth, left, right, magic_of(left), magic_of(left * nqk));
                     double *t = cur; cur = oth; oth = t;
                 }
                 left *= nqk;
@@ -399,7 +491,7 @@ sg4_term_kernel_type10(const PlanDev P, const Op10Dev O, const int npsi,
                     const int total = left * right;
                     for (int o = threadIdx.x; o < total; o += blockDim.x) cur[o] *= s;
                 } else {
-                    mode_product(P.BTw + s_oB[k], nbk, nqk, cur, oth, left, right);
+                    mode_product(P.BTw + s_oB[k], nbk, nqk, cur, oth, left, right, magic_of(left), magic_of(left * nbk));
                     double *t = cur; cur = oth; oth = t;
                 }
                 left *= nbk;

@@ -68,6 +68,7 @@ struct evr_sg4_plan {
     double *d_fmats = nullptr, *d_fV = nullptr;
     evr::FastPlanDev fpd{};
     std::vector<double> h_cost;             // per local term
+    std::vector<int64_t> h_tsize;           // per local term: prod max(nq_k, nb_k)
     int n_classes = 0;
     bool fast_pool_in_smem = false;
     bool fast_block_order = false;
@@ -108,6 +109,51 @@ static int upload(T **dptr, const T *h, size_t n)
     if (n == 0) n = 1;
     CUDA_TRY(cudaMalloc((void **)dptr, n * sizeof(T)));
     if (h) CUDA_TRY(cudaMemcpy(*dptr, h, n * sizeof(T), cudaMemcpyHostToDevice));
+    return 0;
+}
+
+// Size classes of the generic kernel: CTA threads 256 / 128 / 64 / 32 for terms of > 768 / > 192 / > 48 / <= 48
+// values.  Classes of larger terms get a third shared-memory buffer for the mixed-derivative sweeps
+// (want_cache: the operator has mixed terms) when it fits.
+static int gen_class_of(int64_t tsize) { return tsize > 768 ? 0 : (tsize > 192 ? 1 : (tsize > 48 ? 2 : 3)); }
+static int gen_configure(evr_sg4_plan *p, bool want_cache, int n_opterms)
+{
+    static const int class_threads[4] = {256, 128, 64, 32};
+    const int nT = p->D * (p->LG + 1);
+    int cache_classes = 4;                                  // every class (measured best: profiles/shape_bench_r1_generic_v2.txt)
+    if (getenv("EVR_SG4_DCACHE")) cache_classes = atoi(getenv("EVR_SG4_DCACHE"));
+    p->n_gclasses = 0;
+    size_t smem_max = 0;
+    int w0 = 0;
+    for (int c = 0; c < 4; ++c) {
+        int w1 = w0;
+        int64_t ccap = 1;
+        while (w1 < p->n_terms && gen_class_of(p->h_tsize[p->order[w1]]) == c) { ccap = std::max(ccap, p->h_tsize[p->order[w1]] * p->nb0); ++w1; }
+        if (w1 == w0) continue;
+        const int g = p->n_gclasses++;
+        const size_t ints = (size_t)EVR_GEN_SMEM_INTS(nT, p->D, n_opterms) * sizeof(int);
+        bool dc = want_cache && c < cache_classes && (size_t)3 * ccap * sizeof(double) + ints <= 227 * 1024;
+        p->gclass[g].term_begin = w0; p->gclass[g].n_terms = w1 - w0; p->gclass[g].cap = (int)ccap; p->gclass[g].dcache = dc ? 1 : 0;
+        p->gclass_threads[g] = class_threads[c];
+        p->gclass_smem[g] = (size_t)(dc ? 3 : 2) * ccap * sizeof(double) + ints;
+        smem_max = std::max(smem_max, p->gclass_smem[g]);
+        w0 = w1;
+    }
+    if (smem_max > 227 * 1024) return fail("evr_sg4: shared-memory budget exceeded");
+    // the attribute belongs to the function, not to the plan: never lower it under another live plan
+    static size_t attr_max[64] = {0};
+    size_t &amax = attr_max[p->device & 63];
+    amax = std::max(amax, smem_max);
+    if (cudaFuncSetAttribute(evr::sg4_term_kernel_generic, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)amax) != cudaSuccess)
+        return fail("evr_sg4: cudaFuncSetAttribute(smem) failed");
+    for (int g = 0; g < p->n_gclasses; ++g) {
+        int occ = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, evr::sg4_term_kernel_generic, p->gclass_threads[g], p->gclass_smem[g]) != cudaSuccess || occ < 1)
+            return fail("evr_sg4: generic kernel cannot be resident (occupancy 0)");
+        p->gclass_occ[g] = occ;
+    }
+    p->gen_ctas_max = p->n_gclasses ? p->sm_count * p->gclass_occ[0] : p->sm_count;
+    p->grid_ctas = p->n_gclasses ? std::max(1, std::min(p->gclass[0].n_terms, p->gen_ctas_max)) : 1;
     return 0;
 }
 
@@ -224,7 +270,7 @@ extern "C" int evr_sg4_plan_create(evr_sg4_plan **out, int device,
     p->order.resize(p->n_terms);
     std::iota(p->order.begin(), p->order.end(), 0);
     // size classes of the generic kernel (CTA threads 256 / 128 / 64 / 32), then cost descending inside a class
-    auto gclass_of = [&](int t) { return tsize[t] > 768 ? 0 : (tsize[t] > 192 ? 1 : (tsize[t] > 48 ? 2 : 3)); };
+    auto gclass_of = [&](int t) { return gen_class_of(tsize[t]); };
     std::stable_sort(p->order.begin(), p->order.end(), [&](int a, int b) {
         const int ca = gclass_of(a), cb = gclass_of(b);
         return ca != cb ? ca < cb : cost[a] > cost[b];
@@ -268,31 +314,8 @@ extern "C" int evr_sg4_plan_create(evr_sg4_plan **out, int device,
 
     p->smem_bytes = (size_t)2 * p->cap * sizeof(double) + (size_t)(4 * nT + 5 * D) * sizeof(int);
     if (p->smem_bytes > 227 * 1024) { evr_sg4_plan_destroy(&p); return fail("evr_sg4_plan_create: shared-memory budget exceeded"); }
-    if (cudaFuncSetAttribute(evr::sg4_term_kernel_generic, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_bytes) != cudaSuccess) {
-        evr_sg4_plan_destroy(&p); return fail("evr_sg4_plan_create: cudaFuncSetAttribute(smem) failed");
-    }
-    {
-        static const int class_threads[4] = {256, 128, 64, 32};
-        int w0 = 0;
-        for (int c = 0; c < 4; ++c) {
-            int w1 = w0;
-            int64_t ccap = 1;
-            while (w1 < p->n_terms && gclass_of(p->order[w1]) == c) { ccap = std::max(ccap, tsize[p->order[w1]] * nb0); ++w1; }
-            if (w1 == w0) continue;
-            const int g = p->n_gclasses++;
-            p->gclass[g].term_begin = w0; p->gclass[g].n_terms = w1 - w0; p->gclass[g].cap = (int)ccap; p->gclass[g].pad = 0;
-            p->gclass_threads[g] = class_threads[c];
-            p->gclass_smem[g] = (size_t)2 * ccap * sizeof(double) + (size_t)(4 * nT + 5 * D) * sizeof(int);
-            int occ = 0;
-            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, evr::sg4_term_kernel_generic, class_threads[c], p->gclass_smem[g]) != cudaSuccess || occ < 1) {
-                evr_sg4_plan_destroy(&p); return fail("evr_sg4_plan_create: kernel cannot be resident (occupancy 0)");
-            }
-            p->gclass_occ[g] = occ;
-            w0 = w1;
-        }
-        p->gen_ctas_max = p->n_gclasses ? p->sm_count * p->gclass_occ[0] : p->sm_count;
-        p->grid_ctas = p->n_gclasses ? std::max(1, std::min(p->gclass[0].n_terms, p->gen_ctas_max)) : 1;
-    }
+    p->h_tsize = tsize;
+    if (gen_configure(p, false, 0)) { evr_sg4_plan_destroy(&p); return 1; }
 
     evr::PlanDev &pd = p->pd;
     pd.D = D; pd.LG = LG; pd.nb0 = nb0; pd.n_terms = p->n_terms; pd.nb = nb; pd.NQ_local = p->NQ_local;
@@ -676,6 +699,32 @@ extern "C" int evr_sg4_plan_set_op(evr_sg4_plan *p, int type_Op, int nb_Term, co
             const double *src = grids[var_terms[s]] + (size_t)ij * p->NQ_total + p->grid_start;
             CUDA_TRY(cudaMemcpy(p->d_grids + (s * nb0 * nb0 + ij) * blk, src, (size_t)p->NQ_local * sizeof(double), cudaMemcpyHostToDevice));
         }
+    {   // on-the-fly terms first, then the mixed-derivative sweeps grouped by their first mode (sg4_kernels.cuh)
+        std::vector<char> has_sweep(p->D, 0);
+        for (const auto &O : ops) if (O.m1 >= 0 && O.m2 >= 0 && O.m1 != O.m2) has_sweep[O.m1] = 1;
+        auto sweep_of = [&](const evr::OpTermDev &O) {
+            if (O.m1 >= 0 && O.m2 >= 0) return (O.m1 != O.m2) ? O.m1 : -1;
+            const int k = (O.m1 >= 0) ? O.m1 : O.m2;                 // first derivative alone (or none: k = -1)
+            return (k >= 0 && has_sweep[k]) ? k : -1;
+        };
+        std::vector<evr::OpTermDev> sorted;
+        for (const auto &O : ops) if (sweep_of(O) < 0) sorted.push_back(O);
+        p->pd.n_plain = (int)sorted.size();
+        p->pd.n_sweeps = 0;
+        for (int a = 0; a < p->D; ++a) {
+            if (!has_sweep[a]) continue;
+            p->pd.sweep_mode[p->pd.n_sweeps] = a;
+            p->pd.sweep_begin[p->pd.n_sweeps] = (int)sorted.size();
+            for (auto O : ops) if (sweep_of(O) == a) {
+                if (O.m1 != a) std::swap(O.m1, O.m2);               // sweep terms: m1 = cached mode, m2 = other mode or -1
+                sorted.push_back(O);
+            }
+            ++p->pd.n_sweeps;
+        }
+        p->pd.sweep_begin[p->pd.n_sweeps] = (int)sorted.size();
+        ops.swap(sorted);
+        if (gen_configure(p, p->pd.n_sweeps > 0, (int)ops.size())) return 1;
+    }
     if (upload(&p->d_opterms, ops.data(), ops.size())) return 1;
     p->op10 = false;
     p->type_Op = type_Op; p->n_opterms = (int)ops.size(); p->n_var = (int)var_terms.size();

@@ -73,6 +73,33 @@ def test_hno3_shape_curvilinear(evr):
     _check(op, 1)
 
 
+@pytest.mark.parametrize("dcache", ["0", "2", "4"])
+def test_generic_kernel_mixed_derivative_sweeps(evr, dcache, monkeypatch):
+    """Generic kernel: mixed derivatives through the cached first derivative (EVR_SG4_DCACHE = number of size
+    classes that use it: 0 = always on the fly, 4 = every class) with two channels, terms of every size class,
+    and an operator where only some mixed / first-derivative terms are present (others grid_zero / constant)."""
+    monkeypatch.setenv("EVR_SG4_DCACHE", dcache)
+    basis = evr.workloads.hm_sg4_basis(4, 4, 5, [3, 1, 1, 1], [8, 4, 3, 1], nb0=2)
+    assert basis.tab_nq_OF_SRep.max() > 768 and basis.tab_nq_OF_SRep.min() <= 48
+    op = evr.workloads.synthetic_curvilinear(basis)
+    assert op.info(evr.lib.INFO_PATH) == 0
+    _check(op, 2)
+    # sparse operator: drop some terms, make others constant
+    ops = list(op.OpGrid)
+    for it, og in enumerate(ops):
+        d = og.derive_termQact
+        if d in [(1, 3), (2, 0), (2, 2)]:
+            ops[it] = evr.OpGrid(d, grid_zero=True)
+        elif d in [(1, 2), (3, 0), (3, 4)]:
+            ops[it] = evr.OpGrid(d, grid_cte=True, Mat_cte=np.array([[0.3, 0.1], [-0.2, 0.7]]))
+    op2 = evr.ParamOp(basis, 1, ops)
+    assert op2.info(evr.lib.INFO_PATH) == 0
+    _check(op2, 1)
+    part = evr.ParamOp(basis, 1, ops, iG_range=(3, 17))
+    psi = random_psi(basis.nb * 2, 1, 9)
+    assert rel_l2(part.apply_host(psi), oracle_apply(op2, psi, iG_range=(3, 17))) < TOL
+
+
 def test_type_op_0_scalar_operator(evr):
     basis = evr.workloads.hm_sg4_basis(4, 3, 3, 1, 2, nb0=2)
     rng = np.random.default_rng(5)
