@@ -22,56 +22,17 @@
 #pragma once
 #include <cstdint>
 #include "sg4_internal.h"
+#include "sg4_fast_types.h"
 
 namespace evr {
 
-#define EVR_MAXG 8          // max groups (<= 16 active modes) per term on the fast path
-#define EVR_RT_NMAX 16      // runtime-size single-mode tiles keep up to 16 values in registers
-
-struct FastGroup {
-    int stride;             // stride of the first mode of the group (second: stride*n1)
-    unsigned magic;         // floor(2^32/stride)+1 : exact t/stride by __umulhi for t*stride < 2^32 (stride > 1)
-    unsigned short n1, n2;  // n2 = 0: single mode
-    unsigned short tmpl;    // template id (0 = runtime single)
-    unsigned short n3;      // > 0: three-mode cube tile (n1 = n2 = n3)
-    int mat1, mat2, mat3;   // offsets (doubles) of the [B|BTw|T] blocks of the modes in the matrix pool
-};
-
-struct FastTermDev {
-    long long map_off, grid_off;
-    double weight;          // WeightSG * prod_{1x1 modes} B(0,0) BTw(0,0)
-    double vshift;          // sum_{1x1 modes} T(0,0) (+ constant (0,0) term)
-    int nq, ngroups;
-    long long next_map_off, next_grid_off;   // the term this thread group processes next
-    long long next2_map_off;                 // ... and the one after it (software pipeline)
-    int next_nq, next2_nq;
-    FastGroup g[EVR_MAXG];
-};
-
-struct FastClassDev {       // one launch per size class: terms [term_begin, term_begin+n_terms)
-    int term_begin, n_terms;
-    int gsize;              // threads cooperating on one term: 32, 64 or 128
-    int rt;                 // 1: runtime-size tiles (RT instantiation of the kernel)
-    int tri;                // 1: terms with three-mode cube tiles (TRI instantiation, 512 threads)
-    int cap;                // doubles per psi/acc buffer (max nq*nb0 of the class)
-    int cta_threads;        // threads per CTA = groups per CTA * gsize (<= 768)
-};
-
-struct FastPlanDev {
-    int nb0, n_terms, has_V;
-    int pool_len;           // doubles in the (de-duplicated) matrix pool
-    int dbg;                // experiment switch (EVR_SG4_DEBUG): 4 = skip the transform passes
-    long long nb, NQ_local;
-    const FastTermDev *terms;
-    const int32_t *map;     // per term: internal packed index of each entry, sorted ascending (-1 = dropped)
-    const uint16_t *pos;    // per term: term-local position (internal layout) of each sorted entry
-    const double *mats;     // pool of [B|BTw|T] blocks
-    const double *V;        // [nb0*nb0][NQ_local] permuted to the internal layout
-};
-
 // ---- tile primitives -------------------------------------------------------------------------
 // v[i2][i1] register tile; M column-major (n x n): out[q] = sum_b M[q + n*b] in[b]
-template <bool MS>
+// MS: where the 1-D matrices live: 0 = global memory (through L1), 1 = shared-memory pool, 2 = __constant__ array at
+// compile-time offsets (iso flavour: every matrix element becomes a constant-bank operand of its DFMA, no load at all)
+static __constant__ double c_iso[EVR_ISO_LEN];
+template <int N> struct IsoOff { static constexpr int value = iso_off(N); };
+template <int MS>
 __device__ __forceinline__ double ldm(const double *M, int i) { return MS ? M[i] : __ldg(M + i); }
 
 template <int N1, int N2>
@@ -92,7 +53,7 @@ __device__ __forceinline__ void tile_store(const double (&v)[N2][N1], double *bu
 }
 // v <- (M (x) M) v for a square tile whose two modes share one matrix (e.g. equal Hm modes): every matrix
 // row is loaded once and used for both mode products
-template <int N, bool MS>
+template <int N, int MS>
 __device__ __forceinline__ void tile_xform_same(double (&v)[N][N], const double *M)
 {
     double m[N][N];
@@ -120,7 +81,7 @@ __device__ __forceinline__ void tile_xform_same(double (&v)[N][N], const double 
             v[q][i] = s;
         }
 }
-template <int N, bool MS>
+template <int N, int MS>
 __device__ __forceinline__ void tile_keo_same(double (&a)[N][N], const double (&v)[N][N], const double *T)
 {
     double m[N][N];
@@ -141,9 +102,42 @@ __device__ __forceinline__ void tile_keo_same(double (&a)[N][N], const double (&
         }
 }
 // v <- (M2 (x) M1) v        (one matrix ROW is held in registers at a time)
-template <int N1, int N2, bool MS>
+template <int N1, int N2, int MS>
 __device__ __forceinline__ void tile_xform(double (&v)[N2][N1], const double *M1, const double *M2)
 {
+    if constexpr (MS == 2) {
+        // matrix elements are constant-bank operands: no reason to hold a matrix row in registers, so every
+        // pencil is transformed in place (one tile + one pencil of registers live)
+#pragma unroll
+        for (int j = 0; j < N2; ++j) {
+            double t[N1];
+#pragma unroll
+            for (int q = 0; q < N1; ++q) {
+                double s = M1[q] * v[j][0];
+#pragma unroll
+                for (int b = 1; b < N1; ++b) s = fma(M1[q + N1 * b], v[j][b], s);
+                t[q] = s;
+            }
+#pragma unroll
+            for (int q = 0; q < N1; ++q) v[j][q] = t[q];
+        }
+        if (N2 > 1) {
+#pragma unroll
+            for (int i = 0; i < N1; ++i) {
+                double t[N2];
+#pragma unroll
+                for (int q = 0; q < N2; ++q) {
+                    double s = M2[q] * v[0][i];
+#pragma unroll
+                    for (int b = 1; b < N2; ++b) s = fma(M2[q + N2 * b], v[b][i], s);
+                    t[q] = s;
+                }
+#pragma unroll
+                for (int q = 0; q < N2; ++q) v[q][i] = t[q];
+            }
+        }
+        return;
+    }
     if constexpr (N1 == N2 && N1 <= 3) {
         if (M1 == M2) { tile_xform_same<N1, MS>(v, M1); return; }
     }
@@ -189,9 +183,25 @@ __device__ __forceinline__ void tile_xform(double (&v)[N2][N1], const double *M1
     }
 }
 // a += (1 (x) T1 + T2 (x) 1) v
-template <int N1, int N2, bool MS>
+template <int N1, int N2, int MS>
 __device__ __forceinline__ void tile_keo(double (&a)[N2][N1], const double (&v)[N2][N1], const double *T1, const double *T2)
 {
+    if constexpr (MS == 2) {
+#pragma unroll
+        for (int j = 0; j < N2; ++j)
+#pragma unroll
+            for (int q = 0; q < N1; ++q) {
+                double s = a[j][q];
+#pragma unroll
+                for (int b = 0; b < N1; ++b) s = fma(T1[q + N1 * b], v[j][b], s);
+                if (N2 > 1) {
+#pragma unroll
+                    for (int b = 0; b < N2; ++b) s = fma(T2[j + N2 * b], v[b][q], s);
+                }
+                a[j][q] = s;
+            }
+        return;
+    }
     if constexpr (N1 == N2 && N1 <= 3) {
         if (T1 == T2) { tile_keo_same<N1, MS>(a, v, T1); return; }
     }
@@ -247,14 +257,15 @@ __device__ __forceinline__ int tile_origin(const int t, const int stride, const 
     return t + stride * (tile - 1) * hi;           // lo + stride*tile*hi with lo = t - hi*stride
 }
 
-template <int N1, int N2, int KIND, bool MS, bool HV, bool FG, bool SP>
+// S1: the group is the fastest one of the internal layout (stride 1): every tile address is base + immediate
+template <int N1, int N2, int KIND, int MS, bool HV, bool FG, bool SP, bool S1 = false>
 __device__ __forceinline__ void run_pass(const PassArgs &A)
 {
     constexpr int NN1 = N1 * N1, NN2 = N2 * N2, TILE = N1 * N2;
     const int ntiles = A.nq / TILE;
-    const double *__restrict__ B1 = A.pool + A.m1, *__restrict__ W1 = B1 + NN1, *__restrict__ T1 = B1 + 2 * NN1;
-    const double *__restrict__ B2 = A.pool + ((N2 > 1) ? A.m2 : A.m1), *__restrict__ W2 = B2 + NN2, *__restrict__ T2 = B2 + 2 * NN2;
-    const int stride = A.stride;
+    const double *__restrict__ B1 = (MS == 2) ? c_iso + IsoOff<N1>::value : A.pool + A.m1, *__restrict__ W1 = B1 + NN1, *__restrict__ T1 = B1 + 2 * NN1;
+    const double *__restrict__ B2 = (MS == 2) ? c_iso + IsoOff<(N2 > 1 ? N2 : N1)>::value : A.pool + ((N2 > 1) ? A.m2 : A.m1), *__restrict__ W2 = B2 + NN2, *__restrict__ T2 = B2 + 2 * NN2;
+    const int stride = S1 ? 1 : A.stride;
     for (int c = 0; c < A.nb0; ++c) {
         double *__restrict__ psi = A.psi + c * A.nq, *__restrict__ acc = A.acc + c * A.nq;
         for (int t = A.tid; t < ntiles; t += A.nthr) {
@@ -301,7 +312,7 @@ __device__ __forceinline__ void run_pass(const PassArgs &A)
 }
 
 // ---- three-mode cube tiles (N x N x N values per thread, v[k][j][i], strides s, s*N, s*N*N) ----------
-template <int N, bool MS>
+template <int N, int MS>
 __device__ __forceinline__ void load_mat(double (&m)[N][N], const double *M)
 {
 #pragma unroll
@@ -366,7 +377,7 @@ __device__ __forceinline__ void cube_apply2(double (&v)[N][N][N], const double (
             for (int q = 0; q < N; ++q) v[q][j][i] = t[q];
         }
 }
-template <int N, bool MS>
+template <int N, int MS>
 __device__ __forceinline__ void cube_xform(double (&v)[N][N][N], const double *M1, const double *M2, const double *M3)
 {
     double m[N][N];
@@ -379,17 +390,17 @@ __device__ __forceinline__ void cube_xform(double (&v)[N][N][N], const double *M
 }
 
 // cube passes: B2G / G2B in place; LAST and KEO write acc row by row (no second register tile)
-template <int N, int KIND, bool MS, bool HV, bool SP>
+template <int N, int KIND, int MS, bool HV, bool SP, bool S1 = false>
 __device__ __forceinline__ void run_pass_cube(const PassArgs &A)
 {
     constexpr int NN = N * N, TILE = N * N * N;
     const int ntiles = A.nq / TILE;
-    const double *B1 = A.pool + A.m1, *B2 = A.pool + A.m2, *B3 = A.pool + A.m3;
-    const int s1 = A.stride, s2 = A.stride * N, s3 = A.stride * NN;
+    const double *B1 = (MS == 2) ? c_iso + IsoOff<N>::value : A.pool + A.m1, *B2 = (MS == 2) ? B1 : A.pool + A.m2, *B3 = (MS == 2) ? B1 : A.pool + A.m3;
+    const int s1 = S1 ? 1 : A.stride, s2 = s1 * N, s3 = s1 * NN;
     for (int c = 0; c < A.nb0; ++c) {
         double *psi = A.psi + c * A.nq, *acc = A.acc + c * A.nq;
         for (int t = A.tid; t < ntiles; t += A.nthr) {
-            const int q0 = tile_origin(t, A.stride, A.magic, TILE);
+            const int q0 = tile_origin(t, s1, A.magic, TILE);
             double v[N][N][N];
             double *src = (KIND == PASS_G2B) ? acc + q0 : psi + q0;
 #pragma unroll
@@ -445,7 +456,7 @@ __device__ __forceinline__ void run_pass_cube(const PassArgs &A)
 }
 
 // runtime-size single mode (n <= EVR_RT_NMAX): same passes with guarded, unrolled register arrays
-template <bool MS>
+template <int MS>
 __device__ __forceinline__ void run_pass_rt(const PassArgs &A, const int kind, const int n)
 {
     const double *m1 = A.pool + A.m1;
@@ -502,17 +513,25 @@ __device__ __forceinline__ void run_pass_rt(const PassArgs &A, const int kind, c
     }
 }
 
-// template ids (host side uses the same table, sg4_plan.cu: fast_template_id)
-#define EVR_TMPL_LIST(X) X(1, 3, 1) X(2, 5, 1) X(3, 7, 1) X(4, 3, 3) X(7, 2, 1) X(8, 2, 3) X(9, 4, 1) X(10, 2, 2) \
-    X(11, 9, 1) X(12, 11, 1) X(13, 13, 1) X(14, 15, 1) X(15, 6, 1) X(16, 8, 1)
-
-#define EVR_TMPL_CUBE3 30    // template id of the 3x3x3 cube tile (only in the TRI instantiation of the kernel)
-#define EVR_TMPL_CUBE2 31    // 2x2x2
-
-template <int KIND, bool MS, bool RT, bool TRI, bool HV, bool FG, bool SP>
+template <int KIND, int MS, bool RT, bool TRI, bool HV, bool FG, bool SP, bool S1 = false>
 __device__ __forceinline__ void dispatch_pass(const int tmpl, const int n1, const PassArgs &A)
 {
-    if (RT) {                    // terms with a mode size that has no template: runtime-size single-mode tiles only
+    if constexpr (MS == 2) {
+        switch (tmpl) {
+        case 1: run_pass<3, 1, KIND, MS, HV, FG, SP, S1>(A); break;
+        case 2: run_pass<5, 1, KIND, MS, HV, FG, SP, S1>(A); break;
+        case 3: run_pass<7, 1, KIND, MS, HV, FG, SP, S1>(A); break;
+        case 4: run_pass<3, 3, KIND, MS, HV, FG, SP, S1>(A); break;
+        case 20: run_pass<3, 5, KIND, MS, HV, FG, SP, S1>(A); break;
+        // the large tiles (two 21..27-value register tiles in the fused passes) only exist in the 512-thread / 128-register
+        // instantiation (TRI); the 768-thread one keeps to tiles of <= 15 values
+        case 21: if constexpr (TRI) run_pass<3, 7, KIND, MS, HV, FG, SP, S1>(A); break;
+        case 22: if constexpr (TRI) run_pass<3, 9, KIND, MS, HV, FG, SP, S1>(A); break;
+        case 23: if constexpr (TRI) run_pass<5, 5, KIND, MS, HV, FG, SP, S1>(A); break;
+        case EVR_TMPL_CUBE3: if constexpr (TRI) run_pass_cube<3, KIND, MS, HV, SP, S1>(A); break;
+        default: break;          // unreachable: the plan sends terms with other mode sizes to the pool-based instantiations
+        }
+    } else if (RT) {             // terms with a mode size that has no template: runtime-size single-mode tiles only
         run_pass_rt<MS>(A, KIND, n1);
     } else {
         switch (tmpl) {
@@ -544,13 +563,21 @@ __device__ __forceinline__ void cp_async8(void *dst, const void *src)
 {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
 }
+__device__ __forceinline__ void cp_async16(void *dst, const void *src)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+// 8-byte copy, or 8 bytes of zeros when src_bytes == 0 (dropped basis function / padding)
+__device__ __forceinline__ void cp_async8_zfill(void *dst, const void *src, const int src_bytes)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_commit_wait_all() { asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory"); }
 
-#define EVR_FAST_MAX_THREADS 768
-#define EVR_FAST_MAX_THREADS_TRI 512   // cube tiles keep 27 values + a 3x3 matrix in registers: 128 registers per thread
 #define EVR_GB 6            // gather/scatter batch: independent loads in flight per lane
 
-template <bool MS, bool RT, bool TRI>
+template <int MS, bool RT, bool TRI>
 __global__ void __launch_bounds__(TRI ? EVR_FAST_MAX_THREADS_TRI : EVR_FAST_MAX_THREADS, 1)
 sg4_term_kernel_fast(const FastPlanDev P, const FastClassDev Cc, const int npsi,
                      const double *__restrict__ psi, double *__restrict__ Hpsi)
@@ -561,7 +588,7 @@ sg4_term_kernel_fast(const FastPlanDev P, const FastClassDev Cc, const int npsi,
     const int group = threadIdx.x / gsize;
     const int tid = threadIdx.x - group * gsize;
     const int cap = Cc.cap;
-    const int pool_doubles = MS ? P.pool_len : 0;
+    const int pool_doubles = (MS == 1) ? P.pool_len : 0;
     const size_t per_group = (size_t)2 * cap * sizeof(double) + 2 * sizeof(FastTermDev);
     double *s_pool = reinterpret_cast<double *>(smem_raw);
     unsigned char *gbase = smem_raw + (size_t)pool_doubles * sizeof(double) + per_group * group;
@@ -569,11 +596,11 @@ sg4_term_kernel_fast(const FastPlanDev P, const FastClassDev Cc, const int npsi,
     double *s_acc = s_psi + cap;
     FastTermDev *s_T0 = reinterpret_cast<FastTermDev *>(s_acc + cap);
 
-    if (MS) {   // the whole (de-duplicated) 1-D matrix pool lives in shared memory for the kernel's lifetime
+    if (MS == 1) {   // the whole (de-duplicated) 1-D matrix pool lives in shared memory for the kernel's lifetime
         for (int i = threadIdx.x; i < P.pool_len; i += blockDim.x) s_pool[i] = __ldg(P.mats + i);
         __syncthreads();
     }
-    const double *mats = MS ? s_pool : P.mats;
+    const double *mats = (MS == 1) ? s_pool : P.mats;
 
     const int nb0 = P.nb0;
     const long long nvec = P.nb * nb0;
@@ -604,7 +631,9 @@ sg4_term_kernel_fast(const FastPlanDev P, const FastClassDev Cc, const int npsi,
         }
         const FastTermDev *T = s_T0 + ts;
         const int G = (P.dbg & 4) ? 0 : T->ngroups, nq = T->nq;
-        if (npsi == 1 && T->next_nq > 0) {   // pull the next term's mapping / V slices into L2 (links assume npsi = 1)
+        if (npsi == 1 && T->next_nq > 0 && !(P.dbg & 64)) {   // pull the next term's mapping / V slices into L2 (links assume npsi = 1)
+            const char *pg = reinterpret_cast<const char *>(P.gmap + T->next_map_off);
+            for (int b = tid * 128; b < T->next_nq * 4; b += gsize * 128) prefetch_l2(pg + b);
             const char *pm = reinterpret_cast<const char *>(P.map + T->next_map_off);
             for (int b = tid * 128; b < T->next_nq * 4; b += gsize * 128) prefetch_l2(pm + b);
             const char *pq = reinterpret_cast<const char *>(P.pos + T->next_map_off);
@@ -623,36 +652,46 @@ sg4_term_kernel_fast(const FastPlanDev P, const FastClassDev Cc, const int npsi,
             double *y = Hpsi + (long long)ip * nvec;
             // gather (tabPackedBasis_TO_tabR_AT_iG); V of the term goes to the acc buffer, where the
             // LAST pass reads and overwrites it element by element
+            const int32_t *gm = P.gmap + T->map_off;
             if (nb0 == 1) {
-                // batches of EVR_GB elements per lane: all mapping entries of the batch first, then the dependent
-                // packed-psi loads and the V loads (two memory latencies per batch)
-                const int niter = (nq + gsize - 1) / gsize;
-                for (int k0 = 0; k0 < niter; k0 += EVR_GB) {
-                    int mreg[EVR_GB], preg[EVR_GB];
-#pragma unroll
-                    for (int u = 0; u < EVR_GB; ++u) {
-                        const int j = tid + (k0 + u) * gsize;
-                        mreg[u] = (j < nq) ? __ldg(mp + j) : -1;
-                        preg[u] = (j < nq) ? (int)__ldg(pp + j) : 0;
-                    }
-                    double xv[EVR_GB], vv[EVR_GB];
-#pragma unroll
-                    for (int u = 0; u < EVR_GB; ++u) {
-                        const int j = tid + (k0 + u) * gsize;
-                        xv[u] = (mreg[u] >= 0) ? __ldg(x + mreg[u]) : 0.0;
-                        vv[u] = (hasV && j < nq) ? __ldg(Vt + j) : 0.0;
-                    }
-#pragma unroll
-                    for (int u = 0; u < EVR_GB; ++u) {
-                        const int j = tid + (k0 + u) * gsize;
-                        if (j < nq) { s_psi[preg[u]] = xv[u]; if (hasV) s_acc[j] = vv[u]; }
-                    }
+                // Fully asynchronous gather, two memory latencies per term whatever its size:
+                //  (1) the term's slice of the gather map -> acc buffer (16-byte LDGSTS chunks), wait;
+                //  (2) every lane reads its quads of map entries from shared memory and issues the packed-psi copies
+                //      (8-byte LDGSTS, zero-fill for dropped functions / padding) straight into the psi buffer, then - once
+                //      all lanes have read the map - the V slice streams into the acc buffer (16-byte chunks); one wait.
+                const int nq4 = (nq + 3) >> 2;
+                {
+                    const char *src = reinterpret_cast<const char *>(gm);
+                    char *dst = reinterpret_cast<char *>(s_acc);
+                    for (int c = tid; c < nq4; c += gsize) cp_async16(dst + 16 * c, src + 16 * c);
+                    cp_async_commit_wait_all();
+                    group_sync(gsize, group);
                 }
+                {
+                    const int4 *gq = reinterpret_cast<const int4 *>(s_acc);
+                    const bool nox = (P.dbg & 16) != 0;
+                    for (int c = tid; c < nq4; c += gsize) {
+                        const int4 m = gq[c];
+                        double *d = s_psi + 4 * c;
+                        cp_async8_zfill(d, x + max(m.x, 0), (m.x >= 0 && !nox) ? 8 : 0);
+                        cp_async8_zfill(d + 1, x + max(m.y, 0), (m.y >= 0 && !nox) ? 8 : 0);
+                        cp_async8_zfill(d + 2, x + max(m.z, 0), (m.z >= 0 && !nox) ? 8 : 0);
+                        cp_async8_zfill(d + 3, x + max(m.w, 0), (m.w >= 0 && !nox) ? 8 : 0);
+                    }
+                    group_sync(gsize, group);
+                }
+                if (hasV && !(P.dbg & 32)) {
+                    const char *src = reinterpret_cast<const char *>(Vt);
+                    char *dst = reinterpret_cast<char *>(s_acc);
+                    const int nq2 = (nq + 1) >> 1;
+                    for (int c = tid; c < nq2; c += gsize) cp_async16(dst + 16 * c, src + 16 * c);
+                }
+                cp_async_commit_wait_all();
             } else {
                 for (int j = tid; j < nq; j += gsize) {
-                    const int m = __ldg(mp + j), q = __ldg(pp + j);
+                    const int m = __ldg(gm + j);
                     for (int c = 0; c < nb0; ++c)
-                        s_psi[c * nq + q] = (m >= 0) ? __ldg(x + (long long)c * P.nb + m) : 0.0;
+                        s_psi[c * nq + j] = (m >= 0) ? __ldg(x + (long long)c * P.nb + m) : 0.0;
                 }
             }
             group_sync(gsize, group);
@@ -664,13 +703,25 @@ sg4_term_kernel_fast(const FastPlanDev P, const FastClassDev Cc, const int npsi,
                 const FastGroup &Gr = T->g[g];
                 A.stride = Gr.stride; A.magic = Gr.magic; A.m1 = Gr.mat1; A.m2 = Gr.mat2; A.m3 = Gr.mat3;
             };
+            // once the last pass that reads the psi buffer is done, the sorted scatter map (4 B/entry) and the positions
+            // (2 B/entry) of the term stream into that buffer while the remaining G -> B passes run
+            const int nq32 = (nq + 31) & ~31;
+            auto stage_scatter_map = [&]() {
+                char *dst = reinterpret_cast<char *>(s_psi);
+                const char *sm = reinterpret_cast<const char *>(mp), *sp = reinterpret_cast<const char *>(pp);
+                const int c_map = nq32 >> 2, c_all = c_map + (nq32 >> 3);
+                for (int c = tid; c < c_all; c += gsize)
+                    cp_async16(dst + 16 * c, (c < c_map) ? sm + 16 * c : sp + 16 * (c - c_map));
+                cp_async_commit();
+            };
             if (G == 0) {
                 if (tid < nb0) s_acc[tid] = (T->vshift + (hasV ? s_acc[tid] : 0.0)) * s_psi[tid];
                 group_sync(gsize, group);
             } else {
                 for (int g = 0; g < G - 1; ++g) {                 // B -> G (BDP_TO_GDP_OF_SmolyakRep)
                     set_group(g);
-                    dispatch_pass<PASS_B2G, MS, RT, TRI, false, false, false>(T->g[g].tmpl, T->g[g].n1, A);
+                    if (MS == 2 && g == 0) dispatch_pass<PASS_B2G, MS, RT, TRI, false, false, false, MS == 2>(T->g[g].tmpl, T->g[g].n1, A);
+                    else dispatch_pass<PASS_B2G, MS, RT, TRI, false, false, false>(T->g[g].tmpl, T->g[g].n1, A);
                     group_sync(gsize, group);
                 }
                 // last group: B -> G, (V+shift) psi, its kinetic part (, its G -> B when it is the only group)
@@ -682,14 +733,14 @@ sg4_term_kernel_fast(const FastPlanDev P, const FastClassDev Cc, const int npsi,
                 {
                     const int tm = T->g[G - 1].tmpl, n1 = T->g[G - 1].n1;
                     if (A.fuse_g2b) {            // single group, V fused: B->G, V, T, G->B in one pass
-                        if (A.hasV) dispatch_pass<PASS_LAST, MS, RT, TRI, true, true, false>(tm, n1, A);
-                        else dispatch_pass<PASS_LAST, MS, RT, TRI, false, true, false>(tm, n1, A);
+                        if (A.hasV) dispatch_pass<PASS_LAST, MS, RT, TRI, true, true, false, MS == 2>(tm, n1, A);
+                        else dispatch_pass<PASS_LAST, MS, RT, TRI, false, true, false, MS == 2>(tm, n1, A);
                     } else if (A.store_psi) {
                         if (A.hasV) dispatch_pass<PASS_LAST, MS, RT, TRI, true, false, true>(tm, n1, A);
                         else dispatch_pass<PASS_LAST, MS, RT, TRI, false, false, true>(tm, n1, A);
                     } else {                     // single cube group: G->B follows as a separate pass
-                        if (A.hasV) dispatch_pass<PASS_LAST, MS, RT, TRI, true, false, false>(tm, n1, A);
-                        else dispatch_pass<PASS_LAST, MS, RT, TRI, false, false, false>(tm, n1, A);
+                        if (A.hasV) dispatch_pass<PASS_LAST, MS, RT, TRI, true, false, false, MS == 2>(tm, n1, A);
+                        else dispatch_pass<PASS_LAST, MS, RT, TRI, false, false, false, MS == 2>(tm, n1, A);
                     }
                 }
                 A.hasV = 0; A.store_psi = 0;
@@ -712,47 +763,46 @@ sg4_term_kernel_fast(const FastPlanDev P, const FastClassDev Cc, const int npsi,
                 }
                 group_sync(gsize, group);
             }
+            if (G == 0) stage_scatter_map();
             if (G > 0) {
                 // kinetic parts of the other groups; the last one also transforms its group G -> B
                 for (int g = G - 2; g >= 0; --g) {
                     set_group(g);
                     A.fuse_g2b = (g == 0) ? 1 : 0;
-                    if (g == 0 && T->g[0].n3 == 0) dispatch_pass<PASS_KEO, MS, RT, TRI, false, true, false>(T->g[g].tmpl, T->g[g].n1, A);
+                    if (g == 0 && T->g[0].n3 == 0) dispatch_pass<PASS_KEO, MS, RT, TRI, false, true, false, MS == 2>(T->g[g].tmpl, T->g[g].n1, A);
+                    else if (MS == 2 && g == 0) dispatch_pass<PASS_KEO, MS, RT, TRI, false, false, false, MS == 2>(T->g[g].tmpl, T->g[g].n1, A);
                     else dispatch_pass<PASS_KEO, MS, RT, TRI, false, false, false>(T->g[g].tmpl, T->g[g].n1, A);
                     group_sync(gsize, group);
                 }
                 A.fuse_g2b = 0;
+                stage_scatter_map();
                 // remaining G -> B (GDP_TO_BDP_OF_SmolyakRep)
                 const int g_first = (T->g[0].n3 > 0) ? 0 : ((G == 1) ? (v_fused ? 1 : 0) : 1);
                 for (int g = g_first; g < G; ++g) {
                     set_group(g);
-                    dispatch_pass<PASS_G2B, MS, RT, TRI, false, false, false>(T->g[g].tmpl, T->g[g].n1, A);
+                    if (MS == 2 && g == 0) dispatch_pass<PASS_G2B, MS, RT, TRI, false, false, false, MS == 2>(T->g[g].tmpl, T->g[g].n1, A);
+                    else dispatch_pass<PASS_G2B, MS, RT, TRI, false, false, false>(T->g[g].tmpl, T->g[g].n1, A);
                     group_sync(gsize, group);
                 }
             }
-            // weighted scatter-add (tabR_AT_iG_TO_tabPackedBasis)
+            // weighted scatter-add (tabR_AT_iG_TO_tabPackedBasis): sorted entries, one per lane (neighbouring lanes ->
+            // neighbouring addresses, the FP64 reductions of a warp share L2 sectors); map and positions come from the
+            // staged copy in the psi buffer; padding / dropped entries carry index -1
             {
+                cp_async_commit_wait_all();
+                group_sync(gsize, group);
                 const double weight = T->weight;
-                if (nb0 == 1) {
-                    const int niter = (nq + gsize - 1) / gsize;
-                    for (int k0 = 0; k0 < niter; k0 += EVR_GB) {
-                        int mreg[EVR_GB], preg[EVR_GB];
-#pragma unroll
-                        for (int u = 0; u < EVR_GB; ++u) {
-                            const int j = tid + (k0 + u) * gsize;
-                            mreg[u] = (j < nq) ? __ldg(mp + j) : -1;
-                            preg[u] = (j < nq) ? (int)__ldg(pp + j) : 0;
-                        }
-#pragma unroll
-                        for (int u = 0; u < EVR_GB; ++u)
-                            if (mreg[u] >= 0) atomicAdd(y + mreg[u], weight * s_acc[preg[u]]);
-                    }
-                } else {
-                    for (int j = tid; j < nq; j += gsize) {
-                        const int m = __ldg(mp + j), q = __ldg(pp + j);
-                        if (m >= 0)
-                            for (int c = 0; c < nb0; ++c)
-                                atomicAdd(y + (long long)c * P.nb + m, weight * s_acc[c * nq + q]);
+                const int *s_map = reinterpret_cast<const int *>(s_psi);
+                const unsigned short *s_pos = reinterpret_cast<const unsigned short *>(s_psi) + 2 * nq32;
+                const bool nored = (P.dbg & 8) != 0;
+#pragma unroll 4
+                for (int j = tid; j < nq32; j += gsize) {
+                    const int m = s_map[j];
+                    const int q = s_pos[j];
+                    if (m >= 0 && !nored) {
+                        if (nb0 == 1) atomicAdd(y + m, weight * s_acc[q]);
+                        else
+                            for (int c = 0; c < nb0; ++c) atomicAdd(y + (long long)c * P.nb + m, weight * s_acc[c * nq + q]);
                     }
                 }
             }
@@ -762,7 +812,7 @@ sg4_term_kernel_fast(const FastPlanDev P, const FastClassDev Cc, const int npsi,
 }
 
 // packed vectors between the caller's order (RvecB) and the internal block order
-__global__ void sg4_permute_in(const int32_t *__restrict__ perm, const long long nb, const int nvecs,
+static __global__ void sg4_permute_in(const int32_t *__restrict__ perm, const long long nb, const int nvecs,
                                const double *__restrict__ src, double *__restrict__ dst)
 {
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nb; i += (long long)gridDim.x * blockDim.x) {
@@ -770,7 +820,7 @@ __global__ void sg4_permute_in(const int32_t *__restrict__ perm, const long long
         for (int v = 0; v < nvecs; ++v) dst[v * nb + i] = __ldg(src + v * nb + r);
     }
 }
-__global__ void sg4_permute_out(const int32_t *__restrict__ perm, const long long nb, const int nvecs,
+static __global__ void sg4_permute_out(const int32_t *__restrict__ perm, const long long nb, const int nvecs,
                                 const double *__restrict__ src, double *__restrict__ dst)
 {
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nb; i += (long long)gridDim.x * blockDim.x) {

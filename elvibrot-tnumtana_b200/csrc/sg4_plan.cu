@@ -7,7 +7,7 @@
 #include "../../include/evr_sg4.h"
 #include "sg4_internal.h"
 #include "sg4_kernels.cuh"
-#include "sg4_fast.cuh"
+#include "sg4_fast_types.h"
 
 #include <cuda_runtime.h>
 
@@ -61,6 +61,7 @@ struct evr_sg4_plan {
     bool fast = false;
     evr::FastTermDev *d_fterms = nullptr;
     int32_t *d_fmap = nullptr;           // per term: internal packed index (sorted ascending), -1 = dropped
+    int32_t *d_gmap = nullptr;           // per term: internal packed index in term-local (internal layout) order
     uint16_t *d_fpos = nullptr;          // per term: term-local position of each sorted entry
     int32_t *d_perm = nullptr;           // internal packed order -> reference packed index (0-based)
     double *d_psi_int = nullptr, *d_Hpsi_int = nullptr;   // packed vectors in the internal (block) order
@@ -72,9 +73,14 @@ struct evr_sg4_plan {
     int n_classes = 0;
     bool fast_pool_in_smem = false;
     bool fast_block_order = false;
-    evr::FastClassDev fclass[9];
-    size_t fclass_smem[9] = {0};
-    int fclass_ctas[9] = {0};
+    bool fast_iso = false;                  // constant-matrix instantiation (sg4_iso.cu)
+    std::vector<double> iso_blocks;         // its [B|BTw|T] blocks, bound to the __constant__ array before each launch
+    int iso_id = 0;
+    evr::FastClassDev fclass[12];
+    size_t fclass_smem[12] = {0};
+    int fclass_ctas[12] = {0};
+    bool fclass_is_iso[12] = {false};
+    int fclass_flavour[12] = {0};        // 0 templated, 1 runtime-size, 2 cube tiles (plain) / iso with large tiles, 3 iso
     // device
     evr::TermDev *d_terms = nullptr;
     uint8_t *d_lev = nullptr;
@@ -91,8 +97,8 @@ struct evr_sg4_plan {
     int ctas10_max = 0;
     int64_t stage_cap = 0;
     cudaStream_t stream = nullptr;
-    cudaStream_t side[9] = {nullptr};   // class kernels overlap their tails
-    cudaEvent_t ev_fork = nullptr, ev_join[9] = {nullptr};
+    cudaStream_t side[12] = {nullptr};   // class kernels overlap their tails
+    cudaEvent_t ev_fork = nullptr, ev_join[12] = {nullptr};
     size_t smem_bytes = 0;
     int grid_ctas = 0, gen_ctas_max = 0;
     // generic kernel: one launch per term-size class (CTA of 256/128/64/32 threads)
@@ -306,7 +312,7 @@ extern "C" int evr_sg4_plan_create(evr_sg4_plan **out, int device,
     }
     if (!getenv("EVR_SG4_SINGLE_STREAM")) {
         bool ok_ev = cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming) == cudaSuccess;
-        for (int c = 1; c < 9 && ok_ev; ++c)
+        for (int c = 1; c < 12 && ok_ev; ++c)
             ok_ev = cudaStreamCreateWithFlags(&p->side[c], cudaStreamNonBlocking) == cudaSuccess &&
                     cudaEventCreateWithFlags(&p->ev_join[c], cudaEventDisableTiming) == cudaSuccess;
         if (!ok_ev) { evr_sg4_plan_destroy(&p); return fail("evr_sg4_plan_create: side stream/event creation failed"); }
@@ -330,10 +336,11 @@ extern "C" int evr_sg4_plan_create(evr_sg4_plan **out, int device,
 // Fast path set-up (sg4_fast.cuh): returns 0 and sets p->fast when the operator qualifies,
 // returns 0 with p->fast == false when it does not (generic kernel is used), 1 on CUDA errors.
 // ------------------------------------------------------------------------------------------------
-static int fast_template_id(int n1, int n2)
+static int fast_template_id(int n1, int n2, bool iso = false)
 {
 #define X(id, a, b) if (n1 == a && ((b == 1 && n2 == 0) || (b > 1 && n2 == b))) return id;
     EVR_TMPL_LIST(X)
+    if (iso) { EVR_TMPL_LIST_ISO(X) }
 #undef X
     return 0;
 }
@@ -399,14 +406,53 @@ static int build_fast_path(evr_sg4_plan *p, int nb_Term, const int32_t *term_mod
                 pool.insert(pool.end(), blk.begin(), blk.end());
             }
     }
+    if (pool.size() & 1) pool.push_back(0.0);                  // keeps the shared-memory buffers behind the pool 16-byte aligned
     const bool pool_in_smem = pool.size() * sizeof(double) <= 24 * 1024;
+    // iso flavour (sg4_iso.cu): every mode size n >= 2 has exactly ONE [B|BTw|T] block (all modes of that size share
+    // it, e.g. D identical Gauss-Hermite modes) -> the blocks go to a __constant__ array at compile-time offsets
+    bool iso = !getenv("EVR_SG4_ISO") || atoi(getenv("EVR_SG4_ISO")) != 0;
+    const bool iso_big = iso && getenv("EVR_SG4_ISO") && atoi(getenv("EVR_SG4_ISO")) == 2;   // 512-thread instantiation with the large tiles
+    std::vector<double> iso_blocks((size_t)EVR_ISO_LEN, 0.0);
+    {
+        std::vector<int> off_of_n(EVR_ISO_NMAX + 1, -1);
+        bool any = false;
+        for (int i = 0; i < nT && iso; ++i) {
+            const int n = p->h_nq_of[i];
+            if (n < 2) continue;
+            if (n > EVR_ISO_NMAX) { iso = false; break; }
+            if (off_of_n[n] < 0) off_of_n[n] = moff[i];
+            else if (off_of_n[n] != moff[i]) iso = false;
+            any = true;
+        }
+        if (!any) iso = false;
+        if (iso)
+            for (int n = 2; n <= EVR_ISO_NMAX; ++n)
+                if (off_of_n[n] >= 0) std::copy(pool.begin() + off_of_n[n], pool.begin() + off_of_n[n] + 3 * n * n, iso_blocks.begin() + evr::iso_off(n));
+    }
     // per-term schedules + permutation to the internal layout
     // size classes: how many threads cooperate on one term (tiles per pass ~ nq/9 .. nq/21)
     // a term whose active mode sizes all have single-mode templates uses the templated kernel; any other size
     // (<= EVR_RT_NMAX) sends the whole term to the runtime-size instantiation (classes 3..5)
-    std::vector<char> term_rt(p->n_terms, 0);
+    // iso plans: a term runs in the constant-matrix instantiation when its active mode sizes are 3, 5, 7 (with the
+    // large tiles also 9, as long as every 7 and 9 finds a 3 to pair with); the few other terms of such a plan use the
+    // pool-based instantiations like the terms of a non-iso plan
+    std::vector<char> term_rt(p->n_terms, 0), term_iso(p->n_terms, 0);
     for (int t = 0; t < p->n_terms; ++t) {
         const int iG = p->iG_begin + t;
+        int c3 = 0, c79 = 0, cbad = 0, nact = 0;
+        for (int k = 0; k < D; ++k) {
+            const int n = p->h_nq_of[k * (LG + 1) + p->h_tab_l[(size_t)iG * D + k]];
+            if (n < 2) continue;
+            ++nact;
+            if (n == 3) ++c3; else if (n == 7 || (n == 9 && iso_big)) ++c79; else if (n != 5) ++cbad;
+        }
+        term_iso[t] = iso && nact > 0 && cbad == 0;
+        if (iso && iso_big && term_iso[t]) {   // a 9 without a partner 3 has no tile
+            int n9 = 0, n7 = 0;
+            for (int k = 0; k < D; ++k) { const int n = p->h_nq_of[k * (LG + 1) + p->h_tab_l[(size_t)iG * D + k]]; n9 += (n == 9); n7 += (n == 7); }
+            if (n9 > 0 && c3 < n9 + n7) term_iso[t] = 0;
+        }
+        if (term_iso[t]) continue;
         for (int k = 0; k < D; ++k) {
             const int n = p->h_nq_of[k * (LG + 1) + p->h_tab_l[(size_t)iG * D + k]];
             if (n > 1 && fast_template_id(n, 0) == 0) { term_rt[t] = 1; if (n > EVR_RT_NMAX) return 0; }
@@ -416,27 +462,28 @@ static int build_fast_path(evr_sg4_plan *p, int nb_Term, const int32_t *term_mod
     auto envi = [](const char *n, int d) { const char *v = getenv(n); return v ? atoi(v) : d; };
     const int64_t thr0 = envi("EVR_SG4_T0", 1024), thr1 = envi("EVR_SG4_T1", 384);
     // cube tiles (three equal modes of size 3 or 2 per thread): how many cubes minimise the group count of a term
-    const bool use_cubes = envi("EVR_SG4_CUBES", 0) != 0;
+    const bool use_cubes = iso_big || (!iso && envi("EVR_SG4_CUBES", 0) != 0);
     auto n_cubes = [](int c) { return (c == 3 || c == 5 || c == 6) ? c / 3 : (c >= 7 ? (c - 4) / 3 + ((c - 4) % 3 == 2 ? 0 : 0) + 1 : 0); };
     std::vector<char> term_tri(p->n_terms, 0);
     if (use_cubes)
         for (int t = 0; t < p->n_terms; ++t) {
-            if (term_rt[t]) continue;
+            if (term_rt[t] || (iso && !term_iso[t])) continue;
             const int iG = p->iG_begin + t;
             int c3 = 0, c2 = 0;
             for (int k = 0; k < D; ++k) {
                 const int n = p->h_nq_of[k * (LG + 1) + p->h_tab_l[(size_t)iG * D + k]];
                 c3 += (n == 3); c2 += (n == 2);
             }
-            if (n_cubes(c3) > 0 || n_cubes(c2) > 0) term_tri[t] = 1;
+            if (iso_big || n_cubes(c3) > 0 || n_cubes(c2) > 0) term_tri[t] = 1;   // iso with large tiles: every term runs in the cube-capable instantiation
         }
     auto class_of = [&](int t) {
         const int64_t sz = (int64_t)p->h_tab_nq[p->iG_begin + t] * nb0;
-        return (sz > thr0 ? 0 : (sz > thr1 ? 1 : 2)) + (term_rt[t] ? 3 : (term_tri[t] ? 6 : 0));
+        return (sz > thr0 ? 0 : (sz > thr1 ? 1 : 2)) + (term_rt[t] ? 3 : (term_tri[t] ? 6 : (term_iso[t] ? 9 : 0)));
     };
-    const int class_gsize[9] = {envi("EVR_SG4_G0", 128), envi("EVR_SG4_G1", 64), envi("EVR_SG4_G2", 32),
-                                envi("EVR_SG4_G0", 128), envi("EVR_SG4_G1", 64), envi("EVR_SG4_G2", 32),
-                                envi("EVR_SG4_G0T", 64), envi("EVR_SG4_G1T", 32), envi("EVR_SG4_G2T", 32)};
+    const int class_gsize[12] = {envi("EVR_SG4_G0", 128), envi("EVR_SG4_G1", 64), envi("EVR_SG4_G2", 32),
+                                 envi("EVR_SG4_G0", 128), envi("EVR_SG4_G1", 64), envi("EVR_SG4_G2", 32),
+                                 envi("EVR_SG4_G0T", 64), envi("EVR_SG4_G1T", 32), envi("EVR_SG4_G2T", 32),
+                                 envi("EVR_SG4_G0", 128), envi("EVR_SG4_G1", 64), envi("EVR_SG4_G2", 32)};
     std::vector<int> forder(p->n_terms);
     std::iota(forder.begin(), forder.end(), 0);
     std::stable_sort(forder.begin(), forder.end(), [&](int a, int b) {
@@ -471,10 +518,19 @@ static int build_fast_path(evr_sg4_plan *p, int nb_Term, const int32_t *term_mod
         for (int64_t i = 0; i < p->nb; ++i) inv_perm[perm[i]] = (int32_t)i;
     }
     std::vector<evr::FastTermDev> fterms(p->n_terms);
-    std::vector<int32_t> fmap((size_t)std::max<int64_t>(p->S_local, 1));
-    std::vector<uint16_t> fpos((size_t)std::max<int64_t>(p->S_local, 1));
+    // Per-term slices of the fast-path arrays are padded to 32 entries (aligned 128-bit loads, no tail guards):
+    //   gmap : packed index of every term-local entry in the INTERNAL term layout (gather: vector loads, linear stores)
+    //   fmap : the same indices sorted ascending + fpos = their term-local positions (scatter: neighbouring lanes hit
+    //          neighbouring addresses, so the FP64 reductions of a warp share L2 sectors)
+    //   fV   : V in the internal term layout
+    // padding entries: index -1 (skipped), position 0, V = 0.
+    std::vector<int64_t> pad_off(p->n_terms + 1, 0);
+    for (int t = 0; t < p->n_terms; ++t) pad_off[t + 1] = pad_off[t] + (((int64_t)p->h_tab_nq[p->iG_begin + t] + 31) & ~(int64_t)31);
+    const int64_t NQ_pad = std::max<int64_t>(pad_off[p->n_terms], 32);
+    std::vector<int32_t> fmap((size_t)NQ_pad, -1), gmap((size_t)NQ_pad, -1);
+    std::vector<uint16_t> fpos((size_t)NQ_pad, 0);
     std::vector<double> fV;
-    if (Vgrid) fV.resize((size_t)nb0 * nb0 * std::max<int64_t>(p->NQ_local, 1));
+    if (Vgrid) fV.assign((size_t)nb0 * nb0 * NQ_pad, 0.0);
     bool ok = true;
 #pragma omp parallel for schedule(dynamic, 64)
     for (int w = 0; w < p->n_terms; ++w) {
@@ -482,7 +538,7 @@ static int build_fast_path(evr_sg4_plan *p, int nb_Term, const int32_t *term_mod
         const int t = forder[w], iG = p->iG_begin + t;
         evr::FastTermDev &F = fterms[w];
         std::memset(&F, 0, sizeof(F));
-        F.map_off = p->h_map_off[t]; F.grid_off = p->h_grid_off[t];
+        F.map_off = pad_off[t]; F.grid_off = pad_off[t];
         F.nq = p->h_tab_nq[iG];
         double wgt = p->h_weight[iG], shift = c00;
         // active modes (size > 1), sorted by size
@@ -502,7 +558,35 @@ static int build_fast_path(evr_sg4_plan *p, int nb_Term, const int32_t *term_mod
         struct Grp { int a1, a2, a3; };        // indices into act; a2 = -1 single; a3 >= 0 cube
         std::vector<Grp> grp;
         std::vector<char> used(act.size(), 0);
-        if (term_tri[t]) {                     // cubes of equal size-3 (or size-2) modes first
+        if (term_iso[t]) {
+            // tiles of the iso instantiation: 3x3x3, 5x5, 3x5, 3x7, 3x9, 3x3, singles.  Pair every 9 and 7 with a 3,
+            // the 5s with each other (a left-over 5 with a 3), then split the remaining 3s into cubes and pairs.
+            std::vector<int> i3, i5, i79, other;
+            for (size_t a = 0; a < act.size(); ++a) {
+                const int n = act[a].n;
+                (n == 3 ? i3 : n == 5 ? i5 : (n == 7 || n == 9) ? i79 : other).push_back((int)a);
+            }
+            for (int a : i79) {
+                if (iso_big && !i3.empty()) { grp.push_back({i3.back(), a, -1}); i3.pop_back(); }
+                else grp.push_back({a, -1, -1});
+            }
+            while (iso_big && i5.size() >= 2) { grp.push_back({i5[i5.size() - 2], i5[i5.size() - 1], -1}); i5.pop_back(); i5.pop_back(); }
+            while (!iso_big && !i5.empty() && !i3.empty()) { grp.push_back({i3.back(), i5.back(), -1}); i3.pop_back(); i5.pop_back(); }
+            while (!iso_big && !i5.empty()) { grp.push_back({i5.back(), -1, -1}); i5.pop_back(); }
+            if (!i5.empty()) {
+                if (!i3.empty()) { grp.push_back({i3.back(), i5[0], -1}); i3.pop_back(); }
+                else grp.push_back({i5[0], -1, -1});
+            }
+            int r = (int)i3.size();
+            int npairs = iso_big ? ((r % 3 == 1 && r >= 4) ? 2 : (r % 3 == 2 ? 1 : 0)) : r / 2;
+            int ncube = iso_big ? (r - 2 * npairs) / 3 : 0;
+            int at = 0;
+            for (int c = 0; c < ncube; ++c, at += 3) grp.push_back({i3[at], i3[at + 1], i3[at + 2]});
+            for (int c = 0; c < npairs; ++c, at += 2) grp.push_back({i3[at], i3[at + 1], -1});
+            for (; at < r; ++at) grp.push_back({i3[at], -1, -1});
+            for (int a : other) grp.push_back({a, -1, -1});
+            std::fill(used.begin(), used.end(), 1);
+        } else if (term_tri[t]) {                     // cubes of equal size-3 (or size-2) modes first
             for (int sz : {3, 2}) {
                 std::vector<int> idxs;
                 for (size_t a = 0; a < act.size(); ++a) if (act[a].n == sz) idxs.push_back((int)a);
@@ -557,24 +641,27 @@ static int build_fast_path(evr_sg4_plan *p, int nb_Term, const int32_t *term_mod
                 in_n.push_back(A3.n); in_ref.push_back(A3.refstride);
                 stride *= A3.n;
             }
-            Gd.tmpl = term_rt[t] ? 0 : (Gd.n3 == 3 ? EVR_TMPL_CUBE3 : (Gd.n3 == 2 ? EVR_TMPL_CUBE2 : (unsigned short)fast_template_id(Gd.n1, Gd.n2)));
+            Gd.tmpl = term_rt[t] ? 0 : (Gd.n3 == 3 ? EVR_TMPL_CUBE3 : (Gd.n3 == 2 ? EVR_TMPL_CUBE2 : (unsigned short)fast_template_id(Gd.n1, Gd.n2, term_iso[t] != 0)));
             if (!term_rt[t] && Gd.tmpl == 0) ok = false;
         }
         // permutation: internal index q' -> reference index q (odometer over internal modes)
         const int nm = (int)in_n.size();
         std::vector<int> idx(nm, 0);
         int64_t q = 0;
-        const int32_t *msrc = p->h_map.data() + F.map_off;
+        const int32_t *msrc = p->h_map.data() + p->h_map_off[t];
         int32_t *mdst = fmap.data() + F.map_off;
+        int32_t *gdst = gmap.data() + F.map_off;
         uint16_t *pdst = fpos.data() + F.map_off;
+        const int64_t ref_grid_off = p->h_grid_off[t];
         if (F.nq > 65535) { ok = false; continue; }
         std::vector<std::pair<int32_t, uint16_t>> ent((size_t)F.nq);
         for (int qp = 0; qp < F.nq; ++qp) {
             const int32_t m = msrc[q];
             ent[qp] = { m > 0 ? inv_perm[m - 1] : INT32_MAX, (uint16_t)qp };
+            gdst[qp] = m > 0 ? inv_perm[m - 1] : -1;
             if (Vgrid)
                 for (int ij = 0; ij < nb0 * nb0; ++ij)
-                    fV[(size_t)ij * p->NQ_local + F.grid_off + qp] = Vgrid[(size_t)ij * p->NQ_total + p->grid_start + F.grid_off + q];
+                    fV[(size_t)ij * NQ_pad + F.grid_off + qp] = Vgrid[(size_t)ij * p->NQ_total + p->grid_start + ref_grid_off + q];
             for (int m2 = 0; m2 < nm; ++m2) {
                 q += in_ref[m2];
                 if (++idx[m2] < in_n[m2]) break;
@@ -590,25 +677,28 @@ static int build_fast_path(evr_sg4_plan *p, int nb_Term, const int32_t *term_mod
     }
     if (!ok) return 0;
     // launch configuration per size class + "next term" prefetch links
-    CUDA_TRY(cudaFuncSetAttribute(evr::sg4_term_kernel_fast<true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    CUDA_TRY(cudaFuncSetAttribute(evr::sg4_term_kernel_fast<false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    CUDA_TRY(cudaFuncSetAttribute(evr::sg4_term_kernel_fast<true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    CUDA_TRY(cudaFuncSetAttribute(evr::sg4_term_kernel_fast<false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    CUDA_TRY(cudaFuncSetAttribute(evr::sg4_term_kernel_fast<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    CUDA_TRY(cudaFuncSetAttribute(evr::sg4_term_kernel_fast<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    if (evr::fast_set_attributes()) return 1;
+    if (iso && evr::iso_set_attributes()) return 1;
     p->n_classes = 0;
     {
         int w0 = 0;
-        for (int c = 0; c < 9; ++c) {
+        for (int c = 0; c < 12; ++c) {
             int w1 = w0;
             int64_t cap = 1;
             while (w1 < p->n_terms && class_of(forder[w1]) == c) { cap = std::max<int64_t>(cap, (int64_t)fterms[w1].nq * nb0); ++w1; }
             if (w1 == w0) continue;
-            const bool rt = (c >= 3 && c < 6), tri = (c >= 6);
+            {   // the psi buffer also stages the scatter map (6 bytes per entry of the slice padded to 32 entries)
+                int64_t nqmax = 1;
+                for (int w = w0; w < w1; ++w) nqmax = std::max<int64_t>(nqmax, fterms[w].nq);
+                const int64_t nq32 = (nqmax + 31) & ~(int64_t)31;
+                cap = std::max<int64_t>(cap, (nq32 * 3 + 3) / 4);
+            }
+            cap = (cap + 3) & ~(int64_t)3;                      // the gather stores whole quads
+            const bool rt = (c >= 3 && c < 6), tri = (c >= 6 && c < 9), iso_class = iso && (c >= 9 || (tri && iso_big));
             const int gsize = class_gsize[c];
             const int max_threads = tri ? EVR_FAST_MAX_THREADS_TRI : EVR_FAST_MAX_THREADS;
             const size_t per_group = (size_t)2 * cap * sizeof(double) + 2 * sizeof(evr::FastTermDev);
-            const size_t pool_bytes = pool_in_smem ? pool.size() * sizeof(double) : 0;
+            const size_t pool_bytes = (pool_in_smem && !iso_class) ? pool.size() * sizeof(double) : 0;
             const size_t budget = 227 * 1024;
             if (pool_bytes + per_group > budget) return 0;
             int ngrp = (int)std::min<size_t>((budget - pool_bytes) / per_group, (size_t)(max_threads / gsize));
@@ -629,6 +719,8 @@ static int build_fast_path(evr_sg4_plan *p, int nb_Term, const int32_t *term_mod
             evr::FastClassDev &C = p->fclass[p->n_classes];
             C.term_begin = w0; C.n_terms = n; C.gsize = gsize; C.rt = rt ? 1 : 0; C.tri = tri ? 1 : 0; C.cap = (int)cap; C.cta_threads = ngrp * gsize;
             p->fclass_smem[p->n_classes] = smem; p->fclass_ctas[p->n_classes] = ctas;
+            p->fclass_flavour[p->n_classes] = iso_class ? (tri ? 2 : 3) : (rt ? 1 : (tri ? 2 : 0));
+            p->fclass_is_iso[p->n_classes] = iso_class;
             ++p->n_classes;
             w0 = w1;
         }
@@ -637,6 +729,8 @@ static int build_fast_path(evr_sg4_plan *p, int nb_Term, const int32_t *term_mod
     p->d_fterms = nullptr; p->d_fmap = nullptr; p->d_fmats = nullptr; p->d_fV = nullptr;
     if (upload(&p->d_fterms, fterms.data(), fterms.size())) return 1;
     if (upload(&p->d_fmap, fmap.data(), fmap.size())) return 1;
+    cudaFree(p->d_gmap); p->d_gmap = nullptr;
+    if (upload(&p->d_gmap, gmap.data(), gmap.size())) return 1;
     cudaFree(p->d_fpos); p->d_fpos = nullptr; cudaFree(p->d_perm); p->d_perm = nullptr;
     if (upload(&p->d_fpos, fpos.data(), fpos.size())) return 1;
     if (upload(&p->d_perm, perm.data(), perm.size())) return 1;
@@ -645,9 +739,12 @@ static int build_fast_path(evr_sg4_plan *p, int nb_Term, const int32_t *term_mod
     evr::FastPlanDev &f = p->fpd;
     f.nb0 = nb0; f.n_terms = p->n_terms; f.has_V = Vgrid ? 1 : 0; f.pool_len = (int)pool.size();
     p->fast_pool_in_smem = pool_in_smem;
+    p->fast_iso = iso && std::any_of(term_iso.begin(), term_iso.end(), [](char c) { return c != 0; });
+    p->iso_blocks.swap(iso_blocks);
+    { static int next_id = 0; p->iso_id = ++next_id; }
     f.dbg = getenv("EVR_SG4_DEBUG") ? atoi(getenv("EVR_SG4_DEBUG")) : 0;
-    f.nb = p->nb; f.NQ_local = p->NQ_local;
-    f.terms = p->d_fterms; f.map = p->d_fmap; f.pos = p->d_fpos; f.mats = p->d_fmats; f.V = p->d_fV;
+    f.nb = p->nb; f.NQ_local = NQ_pad;      // channel stride of the padded V array
+    f.terms = p->d_fterms; f.gmap = p->d_gmap; f.map = p->d_fmap; f.pos = p->d_fpos; f.mats = p->d_fmats; f.V = p->d_fV;
     p->fast = true;
     return 0;
 }
@@ -807,15 +904,14 @@ static int launch(evr_sg4_plan *p, int npsi, const double *d_psi_user, double *d
             CUDA_TRY(cudaMalloc((void **)&p->d_Hpsi_int, bytes));
             p->int_cap = nvecs * p->nb;
         }
-        const int thr = 256;
-        const int blocks = (int)std::min<int64_t>((p->nb + thr - 1) / thr, 148 * 16);
-        evr::sg4_permute_in<<<blocks, thr, 0, st>>>(p->d_perm, p->nb, (int)nvecs, d_psi_user, p->d_psi_int);
+        evr::fast_permute(true, p->d_perm, p->nb, (int)nvecs, d_psi_user, p->d_psi_int, st);
         p->launches += 1;
         d_psi = p->d_psi_int; d_Hpsi = p->d_Hpsi_int;
     }
     CUDA_TRY(cudaMemsetAsync(d_Hpsi, 0, bytes, st));                 // reference zeroes OpPsi (:765)
     if (p->n_terms > 0) {
         if (p->fast) {
+            if (p->fast_iso && evr::iso_bind(p->device, p->iso_id, p->iso_blocks.data(), st)) return 1;
             const bool multi = p->n_classes > 1 && p->ev_fork != nullptr;
             if (multi) CUDA_TRY(cudaEventRecord(p->ev_fork, st));
             for (int c = 0; c < p->n_classes; ++c) {
@@ -825,12 +921,8 @@ static int launch(evr_sg4_plan *p, int npsi, const double *d_psi_user, double *d
                 const bool ms = p->fast_pool_in_smem, rt = p->fclass[c].rt != 0, tri = p->fclass[c].tri != 0;
                 const int nctas = p->fclass_ctas[c], nthr = p->fclass[c].cta_threads;
                 const size_t sm = p->fclass_smem[c];
-                if (tri && ms)       evr::sg4_term_kernel_fast<true, false, true><<<nctas, nthr, sm, st>>>(p->fpd, p->fclass[c], npsi, d_psi, d_Hpsi);
-                else if (tri)        evr::sg4_term_kernel_fast<false, false, true><<<nctas, nthr, sm, st>>>(p->fpd, p->fclass[c], npsi, d_psi, d_Hpsi);
-                else if (ms && !rt)  evr::sg4_term_kernel_fast<true, false, false><<<nctas, nthr, sm, st>>>(p->fpd, p->fclass[c], npsi, d_psi, d_Hpsi);
-                else if (!ms && !rt) evr::sg4_term_kernel_fast<false, false, false><<<nctas, nthr, sm, st>>>(p->fpd, p->fclass[c], npsi, d_psi, d_Hpsi);
-                else if (ms)         evr::sg4_term_kernel_fast<true, true, false><<<nctas, nthr, sm, st>>>(p->fpd, p->fclass[c], npsi, d_psi, d_Hpsi);
-                else                 evr::sg4_term_kernel_fast<false, true, false><<<nctas, nthr, sm, st>>>(p->fpd, p->fclass[c], npsi, d_psi, d_Hpsi);
+                if (p->fclass_is_iso[c]) { if (evr::iso_launch(tri, nctas, nthr, sm, st, p->fpd, p->fclass[c], npsi, d_psi, d_Hpsi)) return 1; }
+                else if (evr::fast_launch(ms ? 1 : 0, rt, tri, nctas, nthr, sm, st, p->fpd, p->fclass[c], npsi, d_psi, d_Hpsi)) return 1;
                 p->launches += 1;
                 if (multi && c > 0) {
                     CUDA_TRY(cudaEventRecord(p->ev_join[c], st));
@@ -862,9 +954,7 @@ static int launch(evr_sg4_plan *p, int npsi, const double *d_psi_user, double *d
     }
     if (use_int) {
         const int64_t nvecs = (int64_t)npsi * p->nb0;
-        const int thr = 256;
-        const int blocks = (int)std::min<int64_t>((p->nb + thr - 1) / thr, 148 * 16);
-        evr::sg4_permute_out<<<blocks, thr, 0, st>>>(p->d_perm, p->nb, (int)nvecs, p->d_Hpsi_int, d_Hpsi_user);
+        evr::fast_permute(false, p->d_perm, p->nb, (int)nvecs, p->d_Hpsi_int, d_Hpsi_user, st);
         p->launches += 1;
         CUDA_TRY(cudaGetLastError());
     }
@@ -921,6 +1011,7 @@ extern "C" int64_t evr_sg4_plan_info(const evr_sg4_plan *p, int what)
     case EVR_INFO_GRID_CTAS: return p->fast ? p->fclass_ctas[0] : p->grid_ctas;
     case EVR_INFO_PATH: return p->fast ? 1 : 0;
     case EVR_INFO_FLOPS_NPSI1: return p->flops_npsi1;
+    case EVR_INFO_ISO: return (p->fast && p->fast_iso) ? 1 : 0;
     default: return -1;
     }
 }
@@ -934,10 +1025,10 @@ extern "C" int evr_sg4_plan_destroy(evr_sg4_plan **pp)
     cudaFree(p->d_offB); cudaFree(p->d_offG); cudaFree(p->d_B); cudaFree(p->d_BTw); cudaFree(p->d_D1); cudaFree(p->d_D2);
     cudaFree(p->d_opterms); cudaFree(p->d_grids); cudaFree(p->d_psi); cudaFree(p->d_Hpsi);
     cudaFree(p->d_fterms); cudaFree(p->d_fmap); cudaFree(p->d_fmats); cudaFree(p->d_fV);
-    cudaFree(p->d_fpos); cudaFree(p->d_perm); cudaFree(p->d_psi_int); cudaFree(p->d_Hpsi_int);
+    cudaFree(p->d_fpos); cudaFree(p->d_gmap); cudaFree(p->d_perm); cudaFree(p->d_psi_int); cudaFree(p->d_Hpsi_int);
     cudaFree(p->d_GG); cudaFree(p->d_Jac); cudaFree(p->d_sq);
     if (p->stream) cudaStreamDestroy(p->stream);
-    for (int c = 0; c < 9; ++c) { if (p->side[c]) cudaStreamDestroy(p->side[c]); if (p->ev_join[c]) cudaEventDestroy(p->ev_join[c]); }
+    for (int c = 0; c < 12; ++c) { if (p->side[c]) cudaStreamDestroy(p->side[c]); if (p->ev_join[c]) cudaEventDestroy(p->ev_join[c]); }
     if (p->ev_fork) cudaEventDestroy(p->ev_fork);
     delete p;
     *pp = nullptr;

@@ -143,7 +143,8 @@ enum {                           /* 'what' for evr_sg4_plan_info */
     EVR_INFO_SMEM_BYTES      = 5,   /* dynamic shared memory per CTA                   */
     EVR_INFO_GRID_CTAS       = 6,   /* CTAs per launch                                 */
     EVR_INFO_PATH            = 7,   /* 0 = generic term kernel, 1 = constant-KEO fast path */
-    EVR_INFO_FLOPS_NPSI1     = 8    /* algorithmic flops of one H|psi>      */
+    EVR_INFO_FLOPS_NPSI1     = 8,   /* algorithmic flops of one H|psi>      */
+    EVR_INFO_ISO             = 9    /* 1 = fast path runs its constant-matrix instantiation (all modes of a size share one 1-D basis) */
 };
 int64_t evr_sg4_plan_info(const evr_sg4_plan *plan, int what);
 int     evr_sg4_plan_destroy(evr_sg4_plan **plan);

@@ -291,3 +291,45 @@ def test_empty_term_range_and_single_term(evr):
     assert np.abs(empty.apply_host(psi)).max() == 0.0
     one = evr.ParamOp(basis, 1, op.OpGrid, iG_range=(7, 8))
     assert rel_l2(one.apply_host(psi), oracle_apply(op, psi, iG_range=(7, 8))) < TOL
+
+
+def test_iso_flavour_selection_and_agreement_with_plain_fast_path(evr, monkeypatch):
+    """The constant-matrix ("iso") instantiation is selected when all modes of one size share one 1-D basis
+    (Henon-Heiles: D identical Hm modes), not when the kinetic constants differ per mode; both flavours of the fast
+    path give the same H|psi> (same arithmetic, different tiling).  Sizes 9..15 (L up to 7 in 2-D/3-D) run the
+    runtime-size tiles of the iso kernel, even sizes (nq = 2 + L ... ) likewise."""
+    if os.environ.get("EVR_SG4_FORCE_GENERIC") == "1" or "EVR_SG4_ISO" in os.environ:
+        pytest.skip("kernel selection overridden from the environment")
+    for D, L in [(6, 3), (12, 3), (3, 7), (2, 7), (7, 5)]:
+        basis, op = evr.workloads.henon_heiles(D, L)
+        out, ref = _check(op, 2)
+        assert op.info(evr.lib.INFO_PATH) == 1 and op.info(evr.lib.INFO_ISO) == 1
+        monkeypatch.setenv("EVR_SG4_ISO", "0")
+        plain = evr.ParamOp(basis, 1, op.OpGrid)
+        psi = random_psi(basis.nb, 2)
+        o2 = plain.apply_host(psi)
+        assert plain.info(evr.lib.INFO_ISO) == 0 and plain.info(evr.lib.INFO_PATH) == 1
+        monkeypatch.delenv("EVR_SG4_ISO")
+        for i in range(2):
+            assert rel_l2(out[i], o2[i]) < 1e-13
+    # different kinetic constants per mode: one block per (mode, size) -> plain fast path
+    basis = evr.workloads.hm_sg4_basis(6, 3, 3, 1, 2)
+    op = evr.ParamOp(basis, 1, evr.workloads.constant_keo_opgrids(6, 1, np.linspace(0.5, 1.5, 6), None))
+    _check(op, 1)
+    assert op.info(evr.lib.INFO_PATH) == 1 and op.info(evr.lib.INFO_ISO) == 0
+    # mode sizes other than 3, 5, 7 (here nq = nb = 2 + L: 2, 3, 4, 5): those terms use the pool-based instantiations
+    basis = evr.workloads.hm_sg4_basis(5, 3, 3, 2, 1)
+    op = evr.ParamOp(basis, 1, evr.workloads.constant_keo_opgrids(5, 1, np.ones(5), None))
+    _check(op, 2)
+    assert op.info(evr.lib.INFO_ISO) == 0 and op.info(evr.lib.INFO_PATH) == 1
+
+
+def test_two_iso_plans_with_different_bases_alternate(evr):
+    """The iso matrices live in one __constant__ array per device: alternating between plans whose 1-D bases differ
+    must re-bind the array (each result still matches the oracle)."""
+    b1, op1 = evr.workloads.henon_heiles(4, 3)
+    b2 = evr.workloads.hm_sg4_basis(4, 3, 3, 1, 2, scaleQ=1.3)
+    op2 = evr.ParamOp(b2, 1, evr.workloads.constant_keo_opgrids(4, 1, np.ones(4), None))
+    for _ in range(3):
+        _check(op1, 1)
+        _check(op2, 1)
