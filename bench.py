@@ -294,7 +294,7 @@ def main():
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": (traffic or {}).get("dram_bytes_per_launch"), "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg, "kernel_ms": k_ms,
-                "kernel": "sg4_term_kernel (memset of Hpsi + one term-kernel launch per H|psi>)",
+                "kernel": "sg4_term_kernel_fast (permute-in + memset of Hpsi + one launch per term-size class + permute-out, per H|psi>)",
                 "flops_per_launch": op.info(evr.lib.INFO_FLOPS_NPSI1) * npsi}
 
     cpu = None
@@ -313,7 +313,7 @@ def main():
                            "nb": basis.nb, "npsi": npsi, "parallelism": f"terms/{world} ({args.partition}-balanced contiguous ranges) + NCCL allreduce" if world > 1 else "1 GPU",
                            "cache": "operator grid + mapping streamed per step (%.0f MB) > L2; no flush needed" % (alg1 / 1e6)
                            if alg1 > 130e6 else "inputs smaller than L2 (L2-warm numbers)",
-                           "kernel_path": int(op.info(evr.lib.INFO_PATH)), "setup_s": round(t_setup, 2)},
+                           "kernel_path": int(op.info(evr.lib.INFO_PATH)), "iso_flavour": int(op.info(evr.lib.INFO_ISO)), "setup_s": round(t_setup, 2)},
                 "e2e": e2e, "allreduce_ms": allreduce_ms, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks}
         print(json.dumps(line))
     if world > 1:

@@ -522,6 +522,8 @@ __device__ __forceinline__ void dispatch_pass(const int tmpl, const int n1, cons
         case 2: run_pass<5, 1, KIND, MS, HV, FG, SP, S1>(A); break;
         case 3: run_pass<7, 1, KIND, MS, HV, FG, SP, S1>(A); break;
         case 4: run_pass<3, 3, KIND, MS, HV, FG, SP, S1>(A); break;
+        case 11: run_pass<9, 1, KIND, MS, HV, FG, SP, S1>(A); break;
+        case 12: run_pass<11, 1, KIND, MS, HV, FG, SP, S1>(A); break;
         case 20: run_pass<3, 5, KIND, MS, HV, FG, SP, S1>(A); break;
         // the large tiles (two 21..27-value register tiles in the fused passes) only exist in the 512-thread / 128-register
         // instantiation (TRI); the 768-thread one keeps to tiles of <= 15 values
@@ -611,21 +613,24 @@ sg4_term_kernel_fast(const FastPlanDev P, const FastClassDev Cc, const int npsi,
 
     // work item = (term, right-hand side), item w -> term w / npsi, RHS w % npsi: blocks of vectors (Davidson)
     // keep every thread group busy even when the configuration has few Smolyak terms
-    const long long n_items = (long long)Cc.n_terms * npsi;
-    const long long w_first = blockIdx.x * ngrp + group;
+    // (32-bit item arithmetic, and no division at all for a single right-hand side: a 64-bit divide per item is a
+    // ~100-instruction subroutine on the dependent chain of every term)
+    const int n_items = Cc.n_terms * npsi;
+    const int w_first = blockIdx.x * ngrp + group;
+    auto term_of = [&](const int w) { return (npsi == 1) ? w : (int)((unsigned)w / (unsigned)npsi); };
     if (w_first < n_items) {   // first descriptor of this group
-        const double *src = reinterpret_cast<const double *>(terms + (int)(w_first / npsi));
+        const double *src = reinterpret_cast<const double *>(terms + term_of(w_first));
         double *dst = reinterpret_cast<double *>(s_T0);
         for (int i = tid; i < (int)(sizeof(FastTermDev) / 8); i += gsize) cp_async8(dst + i, src + i);
     }
     int ts = 0;
-    for (long long w = w_first; w < n_items; w += step, ts ^= 1) {
-        const int it = (int)(w / npsi);
-        const int ip = (int)(w - (long long)it * npsi);
+    for (int w = w_first; w < n_items; w += step, ts ^= 1) {
+        const int it = term_of(w);
+        const int ip = w - it * npsi;
         cp_async_commit_wait_all();            // descriptor of this item has landed (issued one item ago)
         group_sync(gsize, group);
         if (w + step < n_items) {              // descriptor of the next item -> other slot, asynchronously
-            const double *src = reinterpret_cast<const double *>(terms + (int)((w + step) / npsi));
+            const double *src = reinterpret_cast<const double *>(terms + term_of(w + step));
             double *dst = reinterpret_cast<double *>(s_T0 + (ts ^ 1));
             for (int i = tid; i < (int)(sizeof(FastTermDev) / 8); i += gsize) cp_async8(dst + i, src + i);
         }
@@ -795,15 +800,20 @@ sg4_term_kernel_fast(const FastPlanDev P, const FastClassDev Cc, const int npsi,
                 const int *s_map = reinterpret_cast<const int *>(s_psi);
                 const unsigned short *s_pos = reinterpret_cast<const unsigned short *>(s_psi) + 2 * nq32;
                 const bool nored = (P.dbg & 8) != 0;
-#pragma unroll 4
-                for (int j = tid; j < nq32; j += gsize) {
-                    const int m = s_map[j];
-                    const int q = s_pos[j];
+                // software-pipelined by hand (the entry of the next round is loaded before this round's reduction is
+                // issued); an unrolled loop would need the trip count, i.e. a division by the runtime group size
+                int j = tid;
+                int m = (j < nq32) ? s_map[j] : -1, q = (j < nq32) ? (int)s_pos[j] : 0;
+                while (j < nq32) {
+                    const int jn = j + gsize;
+                    int mn = -1, qn = 0;
+                    if (jn < nq32) { mn = s_map[jn]; qn = s_pos[jn]; }
                     if (m >= 0 && !nored) {
                         if (nb0 == 1) atomicAdd(y + m, weight * s_acc[q]);
                         else
                             for (int c = 0; c < nb0; ++c) atomicAdd(y + (long long)c * P.nb + m, weight * s_acc[c * nq + q]);
                     }
+                    m = mn; q = qn; j = jn;
                 }
             }
             group_sync(gsize, group);

@@ -76,11 +76,11 @@ struct evr_sg4_plan {
     bool fast_iso = false;                  // constant-matrix instantiation (sg4_iso.cu)
     std::vector<double> iso_blocks;         // its [B|BTw|T] blocks, bound to the __constant__ array before each launch
     int iso_id = 0;
-    evr::FastClassDev fclass[12];
-    size_t fclass_smem[12] = {0};
-    int fclass_ctas[12] = {0};
-    bool fclass_is_iso[12] = {false};
-    int fclass_flavour[12] = {0};        // 0 templated, 1 runtime-size, 2 cube tiles (plain) / iso with large tiles, 3 iso
+    evr::FastClassDev fclass[13];
+    size_t fclass_smem[13] = {0};
+    int fclass_ctas[13] = {0};
+    bool fclass_is_iso[13] = {false};
+    int fclass_flavour[13] = {0};        // 0 templated, 1 runtime-size, 2 cube tiles (plain) / iso with large tiles, 3 iso
     // device
     evr::TermDev *d_terms = nullptr;
     uint8_t *d_lev = nullptr;
@@ -97,8 +97,8 @@ struct evr_sg4_plan {
     int ctas10_max = 0;
     int64_t stage_cap = 0;
     cudaStream_t stream = nullptr;
-    cudaStream_t side[12] = {nullptr};   // class kernels overlap their tails
-    cudaEvent_t ev_fork = nullptr, ev_join[12] = {nullptr};
+    cudaStream_t side[13] = {nullptr};   // class kernels overlap their tails
+    cudaEvent_t ev_fork = nullptr, ev_join[13] = {nullptr};
     size_t smem_bytes = 0;
     int grid_ctas = 0, gen_ctas_max = 0;
     // generic kernel: one launch per term-size class (CTA of 256/128/64/32 threads)
@@ -312,7 +312,7 @@ extern "C" int evr_sg4_plan_create(evr_sg4_plan **out, int device,
     }
     if (!getenv("EVR_SG4_SINGLE_STREAM")) {
         bool ok_ev = cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming) == cudaSuccess;
-        for (int c = 1; c < 12 && ok_ev; ++c)
+        for (int c = 1; c < 13 && ok_ev; ++c)
             ok_ev = cudaStreamCreateWithFlags(&p->side[c], cudaStreamNonBlocking) == cudaSuccess &&
                     cudaEventCreateWithFlags(&p->ev_join[c], cudaEventDisableTiming) == cudaSuccess;
         if (!ok_ev) { evr_sg4_plan_destroy(&p); return fail("evr_sg4_plan_create: side stream/event creation failed"); }
@@ -433,9 +433,8 @@ static int build_fast_path(evr_sg4_plan *p, int nb_Term, const int32_t *term_mod
     // size classes: how many threads cooperate on one term (tiles per pass ~ nq/9 .. nq/21)
     // a term whose active mode sizes all have single-mode templates uses the templated kernel; any other size
     // (<= EVR_RT_NMAX) sends the whole term to the runtime-size instantiation (classes 3..5)
-    // iso plans: a term runs in the constant-matrix instantiation when its active mode sizes are 3, 5, 7 (with the
-    // large tiles also 9, as long as every 7 and 9 finds a 3 to pair with); the few other terms of such a plan use the
-    // pool-based instantiations like the terms of a non-iso plan
+    // iso plans: a term runs in the constant-matrix instantiation when its active mode sizes are 3, 5, 7, 9 or 11; the
+    // few other terms of such a plan use the pool-based instantiations like the terms of a non-iso plan
     std::vector<char> term_rt(p->n_terms, 0), term_iso(p->n_terms, 0);
     for (int t = 0; t < p->n_terms; ++t) {
         const int iG = p->iG_begin + t;
@@ -444,14 +443,9 @@ static int build_fast_path(evr_sg4_plan *p, int nb_Term, const int32_t *term_mod
             const int n = p->h_nq_of[k * (LG + 1) + p->h_tab_l[(size_t)iG * D + k]];
             if (n < 2) continue;
             ++nact;
-            if (n == 3) ++c3; else if (n == 7 || (n == 9 && iso_big)) ++c79; else if (n != 5) ++cbad;
+            if (n == 3) ++c3; else if (n == 7 || (n == 9 && iso_big)) ++c79; else if (n != 5 && n != 9 && n != 11) ++cbad;
         }
         term_iso[t] = iso && nact > 0 && cbad == 0;
-        if (iso && iso_big && term_iso[t]) {   // a 9 without a partner 3 has no tile
-            int n9 = 0, n7 = 0;
-            for (int k = 0; k < D; ++k) { const int n = p->h_nq_of[k * (LG + 1) + p->h_tab_l[(size_t)iG * D + k]]; n9 += (n == 9); n7 += (n == 7); }
-            if (n9 > 0 && c3 < n9 + n7) term_iso[t] = 0;
-        }
         if (term_iso[t]) continue;
         for (int k = 0; k < D; ++k) {
             const int n = p->h_nq_of[k * (LG + 1) + p->h_tab_l[(size_t)iG * D + k]];
@@ -460,7 +454,7 @@ static int build_fast_path(evr_sg4_plan *p, int nb_Term, const int32_t *term_mod
     }
     // size classes and threads per term (tunable for experiments: EVR_SG4_T0/T1 thresholds, EVR_SG4_G0/G1/G2 group sizes)
     auto envi = [](const char *n, int d) { const char *v = getenv(n); return v ? atoi(v) : d; };
-    const int64_t thr0 = envi("EVR_SG4_T0", 1024), thr1 = envi("EVR_SG4_T1", 384);
+    const int64_t thr0 = envi("EVR_SG4_T0", iso ? 700 : 1024), thr1 = envi("EVR_SG4_T1", 384), thrA = envi("EVR_SG4_TA", 2000);
     // cube tiles (three equal modes of size 3 or 2 per thread): how many cubes minimise the group count of a term
     const bool use_cubes = iso_big || (!iso && envi("EVR_SG4_CUBES", 0) != 0);
     auto n_cubes = [](int c) { return (c == 3 || c == 5 || c == 6) ? c / 3 : (c >= 7 ? (c - 4) / 3 + ((c - 4) % 3 == 2 ? 0 : 0) + 1 : 0); };
@@ -478,17 +472,20 @@ static int build_fast_path(evr_sg4_plan *p, int nb_Term, const int32_t *term_mod
         }
     auto class_of = [&](int t) {
         const int64_t sz = (int64_t)p->h_tab_nq[p->iG_begin + t] * nb0;
+        // iso (768-thread) flavour: a fourth size class for the very largest terms, so that the shared-memory buffers of the
+        // next class are sized for e.g. 1215 instead of 2187 points and almost twice as many of its terms are in flight per SM
+        if (term_iso[t] && !term_tri[t] && sz > thrA) return 12;
         return (sz > thr0 ? 0 : (sz > thr1 ? 1 : 2)) + (term_rt[t] ? 3 : (term_tri[t] ? 6 : (term_iso[t] ? 9 : 0)));
     };
-    const int class_gsize[12] = {envi("EVR_SG4_G0", 128), envi("EVR_SG4_G1", 64), envi("EVR_SG4_G2", 32),
+    const int class_gsize[13] = {envi("EVR_SG4_G0", 128), envi("EVR_SG4_G1", 64), envi("EVR_SG4_G2", 32),
                                  envi("EVR_SG4_G0", 128), envi("EVR_SG4_G1", 64), envi("EVR_SG4_G2", 32),
                                  envi("EVR_SG4_G0T", 64), envi("EVR_SG4_G1T", 32), envi("EVR_SG4_G2T", 32),
-                                 envi("EVR_SG4_G0", 128), envi("EVR_SG4_G1", 64), envi("EVR_SG4_G2", 32)};
+                                 envi("EVR_SG4_G0", 64), envi("EVR_SG4_G1", 32), envi("EVR_SG4_G2", 32), envi("EVR_SG4_GA", 128)};
     std::vector<int> forder(p->n_terms);
     std::iota(forder.begin(), forder.end(), 0);
     std::stable_sort(forder.begin(), forder.end(), [&](int a, int b) {
-        const int ca = class_of(a), cb = class_of(b);
-        if (ca != cb) return ca < cb;
+        const int ca = class_of(a) % 12, cb = class_of(b) % 12;   // class 12 (largest iso terms) is launched first
+        if (class_of(a) != class_of(b)) return (ca != cb) ? ca < cb : class_of(a) > class_of(b);
         return p->h_cost[a] > p->h_cost[b];
     });
     // ---- internal order of the packed vector: functions reached by exactly the same set of Smolyak terms
@@ -682,7 +679,8 @@ static int build_fast_path(evr_sg4_plan *p, int nb_Term, const int32_t *term_mod
     p->n_classes = 0;
     {
         int w0 = 0;
-        for (int c = 0; c < 12; ++c) {
+        for (int ci = 0; ci < 13; ++ci) {
+            const int c = (ci == 0) ? 12 : ci - 1;              // same order as the sort above
             int w1 = w0;
             int64_t cap = 1;
             while (w1 < p->n_terms && class_of(forder[w1]) == c) { cap = std::max<int64_t>(cap, (int64_t)fterms[w1].nq * nb0); ++w1; }
@@ -743,6 +741,9 @@ static int build_fast_path(evr_sg4_plan *p, int nb_Term, const int32_t *term_mod
     p->iso_blocks.swap(iso_blocks);
     { static int next_id = 0; p->iso_id = ++next_id; }
     f.dbg = getenv("EVR_SG4_DEBUG") ? atoi(getenv("EVR_SG4_DEBUG")) : 0;
+    // the L2 prefetch of the next term's slices stopped paying once the slices stream through LDGSTS (measured: equal
+    // times); off unless EVR_SG4_PREFETCH=1
+    if (!getenv("EVR_SG4_PREFETCH") || atoi(getenv("EVR_SG4_PREFETCH")) == 0) f.dbg |= 64;
     f.nb = p->nb; f.NQ_local = NQ_pad;      // channel stride of the padded V array
     f.terms = p->d_fterms; f.gmap = p->d_gmap; f.map = p->d_fmap; f.pos = p->d_fpos; f.mats = p->d_fmats; f.V = p->d_fV;
     p->fast = true;
@@ -911,6 +912,7 @@ static int launch(evr_sg4_plan *p, int npsi, const double *d_psi_user, double *d
     CUDA_TRY(cudaMemsetAsync(d_Hpsi, 0, bytes, st));                 // reference zeroes OpPsi (:765)
     if (p->n_terms > 0) {
         if (p->fast) {
+            if ((long long)p->n_terms * npsi > INT_MAX) return fail("evr_sg4_apply: n_terms * npsi exceeds 2^31 work items");
             if (p->fast_iso && evr::iso_bind(p->device, p->iso_id, p->iso_blocks.data(), st)) return 1;
             const bool multi = p->n_classes > 1 && p->ev_fork != nullptr;
             if (multi) CUDA_TRY(cudaEventRecord(p->ev_fork, st));
@@ -1028,7 +1030,7 @@ extern "C" int evr_sg4_plan_destroy(evr_sg4_plan **pp)
     cudaFree(p->d_fpos); cudaFree(p->d_gmap); cudaFree(p->d_perm); cudaFree(p->d_psi_int); cudaFree(p->d_Hpsi_int);
     cudaFree(p->d_GG); cudaFree(p->d_Jac); cudaFree(p->d_sq);
     if (p->stream) cudaStreamDestroy(p->stream);
-    for (int c = 0; c < 12; ++c) { if (p->side[c]) cudaStreamDestroy(p->side[c]); if (p->ev_join[c]) cudaEventDestroy(p->ev_join[c]); }
+    for (int c = 0; c < 13; ++c) { if (p->side[c]) cudaStreamDestroy(p->side[c]); if (p->ev_join[c]) cudaEventDestroy(p->ev_join[c]); }
     if (p->ev_fork) cudaEventDestroy(p->ev_fork);
     delete p;
     *pp = nullptr;
