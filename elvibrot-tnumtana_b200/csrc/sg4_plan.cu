@@ -890,7 +890,30 @@ extern "C" int evr_sg4_plan_set_op10(evr_sg4_plan *p, int n_act, const int32_t *
     return 0;
 }
 
-static int launch(evr_sg4_plan *p, int npsi, const double *d_psi_user, double *d_Hpsi_user, cudaStream_t st)
+// sub_scaledOpPsi (sub_OpPsi.f90:2823-2866) on the device: y <- (y - E0 x) / Esc, optionally while un-permuting the
+// block-ordered internal result (src[v*nb + i] -> dst[v*nb + perm[i]])
+namespace evr {
+__global__ void sg4_scale_kernel(const long long n, const double E0, const double Esc,
+                                 const double *__restrict__ x, double *__restrict__ y)
+{
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        y[i] = (y[i] - E0 * __ldg(x + i)) / Esc;
+}
+__global__ void sg4_permute_out_scaled(const int32_t *__restrict__ perm, const long long nb, const int nvecs,
+                                       const double E0, const double Esc, const double *__restrict__ x_user,
+                                       const double *__restrict__ src, double *__restrict__ dst)
+{
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nb; i += (long long)gridDim.x * blockDim.x) {
+        const int r = __ldg(perm + i);
+        for (int v = 0; v < nvecs; ++v) dst[v * nb + r] = (src[v * nb + i] - E0 * __ldg(x_user + v * nb + r)) / Esc;
+    }
+}
+}
+
+struct ScaleArgs { bool on; double E0, Esc; };
+
+static int launch(evr_sg4_plan *p, int npsi, const double *d_psi_user, double *d_Hpsi_user, cudaStream_t st,
+                  const ScaleArgs sc = ScaleArgs{false, 0.0, 1.0})
 {
     const size_t bytes = (size_t)npsi * p->nb * p->nb0 * sizeof(double);
     const double *d_psi = d_psi_user;
@@ -956,7 +979,18 @@ static int launch(evr_sg4_plan *p, int npsi, const double *d_psi_user, double *d
     }
     if (use_int) {
         const int64_t nvecs = (int64_t)npsi * p->nb0;
-        evr::fast_permute(false, p->d_perm, p->nb, (int)nvecs, p->d_Hpsi_int, d_Hpsi_user, st);
+        if (sc.on) {
+            const int thr = 256;
+            const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>((p->nb + thr - 1) / thr, 148 * 16));
+            evr::sg4_permute_out_scaled<<<blocks, thr, 0, st>>>(p->d_perm, p->nb, (int)nvecs, sc.E0, sc.Esc, d_psi_user, p->d_Hpsi_int, d_Hpsi_user);
+        } else evr::fast_permute(false, p->d_perm, p->nb, (int)nvecs, p->d_Hpsi_int, d_Hpsi_user, st);
+        p->launches += 1;
+        CUDA_TRY(cudaGetLastError());
+    } else if (sc.on) {
+        const long long n = (long long)npsi * p->nb * p->nb0;
+        const int thr = 256;
+        const int blocks = (int)std::max<long long>(1, std::min<long long>((n + thr - 1) / thr, 148 * 16));
+        evr::sg4_scale_kernel<<<blocks, thr, 0, st>>>(n, sc.E0, sc.Esc, d_psi_user, d_Hpsi_user);
         p->launches += 1;
         CUDA_TRY(cudaGetLastError());
     }
@@ -971,6 +1005,19 @@ extern "C" int evr_sg4_apply_device(evr_sg4_plan *p, int npsi, const double *d_p
     if (!d_psi || !d_Hpsi) return fail("evr_sg4_apply_device: null buffer");
     CUDA_TRY(cudaSetDevice(p->device));
     return launch(p, npsi, d_psi, d_Hpsi, (cudaStream_t)cuda_stream);
+}
+
+extern "C" int evr_sg4_apply_device_scaled(evr_sg4_plan *p, int npsi, const double *d_psi, double *d_Hpsi,
+                                           double E0, double Esc, void *cuda_stream)
+{
+    if (!p) return fail("evr_sg4_apply_device_scaled: null plan");
+    if (!p->op_set) return fail("evr_sg4_apply_device_scaled: operator not set (call evr_sg4_plan_set_op)");
+    if (npsi < 1) return fail("evr_sg4_apply: size(Psi) = 0");
+    if (!d_psi || !d_Hpsi) return fail("evr_sg4_apply_device_scaled: null buffer");
+    if (d_psi == d_Hpsi) return fail("evr_sg4_apply_device_scaled: psi and Hpsi must be different buffers");
+    if (Esc == 0.0) return fail("evr_sg4_apply_device_scaled: Esc = 0");
+    CUDA_TRY(cudaSetDevice(p->device));
+    return launch(p, npsi, d_psi, d_Hpsi, (cudaStream_t)cuda_stream, ScaleArgs{true, E0, Esc});
 }
 
 extern "C" int evr_sg4_apply(evr_sg4_plan *p, int npsi, const double *psi, double *Hpsi)

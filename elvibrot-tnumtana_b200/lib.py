@@ -24,7 +24,7 @@ EXPORTS = [
     "evr_sg4_version", "evr_sg4_last_error",
     "evr_sg4_tables_build", "evr_sg4_tables_destroy", "evr_sg4_tables_size", "evr_sg4_tables_get",
     "evr_sg4_ini_iGs", "evr_sg4_balanced_iGs",
-    "evr_sg4_plan_create", "evr_sg4_plan_set_op", "evr_sg4_plan_set_op10", "evr_sg4_apply", "evr_sg4_apply_device",
+    "evr_sg4_plan_create", "evr_sg4_plan_set_op", "evr_sg4_plan_set_op10", "evr_sg4_apply", "evr_sg4_apply_device", "evr_sg4_apply_device_scaled",
     "evr_sg4_plan_info", "evr_sg4_plan_destroy",
 ]
 
@@ -80,6 +80,8 @@ def lib():
     L.evr_sg4_apply.argtypes = [vp, i32, vp, vp]
     L.evr_sg4_apply_device.restype = i32
     L.evr_sg4_apply_device.argtypes = [vp, i32, vp, vp, vp]
+    L.evr_sg4_apply_device_scaled.restype = i32
+    L.evr_sg4_apply_device_scaled.argtypes = [vp, i32, vp, vp, C.c_double, C.c_double, vp]
     L.evr_sg4_plan_info.restype = i64
     L.evr_sg4_plan_info.argtypes = [vp, i32]
     L.evr_sg4_plan_destroy.restype = i32

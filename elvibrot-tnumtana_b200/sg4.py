@@ -260,6 +260,12 @@ class ParamOp:
         _lib.check(_lib.lib().evr_sg4_apply_device(self.plan(), npsi, d_psi, d_Hpsi, stream), "evr_sg4_apply_device")
         self.nb_OpPsi += npsi
 
+    def apply_device_scaled_ptr(self, npsi: int, d_psi: int, d_Hpsi: int, E0: float, Esc: float, stream: int = 0):
+        """Device-resident H|psi> + sub_scaledOpPsi in one call: Hpsi <- (H psi - E0 psi)/Esc (sub_OpPsi.f90:2823-2866)."""
+        _lib.check(_lib.lib().evr_sg4_apply_device_scaled(self.plan(), npsi, d_psi, d_Hpsi, float(E0), float(Esc), stream),
+                   "evr_sg4_apply_device_scaled")
+        self.nb_OpPsi += npsi
+
 
 class ParamOp10(ParamOp):
     """param_Op with type_Op = 10 and the metric tensor cached per grid point:

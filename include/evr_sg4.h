@@ -132,7 +132,16 @@ int evr_sg4_plan_set_op10(evr_sg4_plan *plan, int n_act, const int32_t *act_mode
  * this rank's partial sum (to be summed over ranks: MPI_Reduce_sum_Bcast / NCCL). */
 int evr_sg4_apply(evr_sg4_plan *plan, int npsi, const double *psi, double *Hpsi);          /* host buffers   */
 int evr_sg4_apply_device(evr_sg4_plan *plan, int npsi, const double *d_psi, double *d_Hpsi,
-                         void *cuda_stream);                                               /* device buffers */
+                         void *cuda_stream);
+
+/* Device-resident H|psi> followed by the Chebyshev / SIL scaling of sub_scaledOpPsi
+ * (Source_ElVibRot/sub_Operator/sub_OpPsi.f90:2823-2866):   Hpsi <- (H psi - E0 psi) / Esc
+ * in one call: the propagators apply this after every H|psi> (sub_module_propa_march.f90:4294-4345), so with the
+ * vectors resident on the device no host round trip remains in the recursion.  On the fast path
+ * with the block-ordered internal vector the scaling is fused into the kernel that writes the result back in
+ * the caller's order; otherwise it is one extra element-wise kernel.  Esc must not be 0. */
+int evr_sg4_apply_device_scaled(evr_sg4_plan *plan, int npsi, const double *d_psi, double *d_Hpsi,
+                                double E0, double Esc, void *cuda_stream);                                               /* device buffers */
 
 enum {                           /* 'what' for evr_sg4_plan_info */
     EVR_INFO_LAUNCHES        = 0,   /* kernels launched by this plan so far            */

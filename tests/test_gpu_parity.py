@@ -333,3 +333,41 @@ def test_two_iso_plans_with_different_bases_alternate(evr):
     for _ in range(3):
         _check(op1, 1)
         _check(op2, 1)
+
+
+def test_device_scaled_entry_point_chebyshev_step(evr, monkeypatch):
+    """evr_sg4_apply_device_scaled = H|psi> followed by sub_scaledOpPsi (sub_OpPsi.f90:2823-2866) on the device:
+    (H psi - E0 psi)/Esc, checked against the oracle for the plain, the block-ordered (fused into the un-permute
+    kernel) and the generic path, plus three steps of the Chebyshev recursion of the propagator
+    (phi_{k+1} = 2 Hs phi_k - phi_{k-1}, sub_module_propa_march.f90:4294-4345) with vectors resident on the device."""
+    import torch
+    E0, Esc = 0.37, 2.5
+    st = torch.cuda.current_stream().cuda_stream
+    for env in ({}, {"EVR_SG4_BLOCK_ORDER": "1"}, {"EVR_SG4_FORCE_GENERIC": "1"}):
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        basis, op = evr.workloads.henon_heiles(6, 3)
+        for k in env:
+            monkeypatch.delenv(k)
+        psi = random_psi(basis.nb, 2, 17)
+        ref = (oracle_apply(op, psi) - E0 * psi) / Esc
+        d_psi = torch.from_numpy(psi).cuda()
+        d_out = torch.full_like(d_psi, -3.0)
+        op.apply_device_scaled_ptr(2, d_psi.data_ptr(), d_out.data_ptr(), E0, Esc, st)
+        torch.cuda.synchronize()
+        out = d_out.cpu().numpy()
+        for i in range(2):
+            assert rel_l2(out[i], ref[i]) < TOL
+        # Chebyshev recursion on the device vs the same recursion with the oracle on the host
+        p0, p1 = d_psi[:1].clone(), d_out[:1].clone()
+        h0, h1 = psi[:1].copy(), ref[:1].copy()
+        for _ in range(3):
+            d_t = torch.empty_like(p1)
+            op.apply_device_scaled_ptr(1, p1.data_ptr(), d_t.data_ptr(), E0, Esc, st)
+            p0, p1 = p1, 2.0 * d_t - p0
+            ht = (oracle_apply(op, h1) - E0 * h1) / Esc
+            h0, h1 = h1, 2.0 * ht - h0
+        torch.cuda.synchronize()
+        assert rel_l2(p1.cpu().numpy()[0], h1[0]) < 1e-11
+    with pytest.raises(Exception):
+        op.apply_device_scaled_ptr(1, d_psi.data_ptr(), d_out.data_ptr(), 0.0, 0.0, st)
