@@ -39,7 +39,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     srcs = [os.path.join(srcdir, f) for f in os.listdir(srcdir)] + [os.path.join(_HERE, "..", "include", "evr_sg4.h")]
     stale = (not os.path.exists(SO_PATH)) or any(os.path.getmtime(s) > os.path.getmtime(SO_PATH) for s in srcs)
     if force or stale:
-        cmd = ["make", "-j", "4", "-C", srcdir] + (["-B"] if force else [])
+        cmd = ["make", "-j", "5", "-C", srcdir] + (["-B"] if force else [])
         out = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
         if verbose or out.returncode != 0:
             print(out.stdout)

@@ -371,3 +371,13 @@ def test_device_scaled_entry_point_chebyshev_step(evr, monkeypatch):
         assert rel_l2(p1.cpu().numpy()[0], h1[0]) < 1e-11
     with pytest.raises(Exception):
         op.apply_device_scaled_ptr(1, d_psi.data_ptr(), d_out.data_ptr(), 0.0, 0.0, st)
+
+
+def test_fast_path_with_matrix_pool_in_global_memory(evr):
+    """Eight modes with eight different scalings and L = 4: 8 x 5 distinct [B|BTw|T] blocks = 32 KB, more than the
+    24 KB shared-memory pool -> the instantiations that read the pool from global memory (sg4_fast_inst0.cu)."""
+    basis = evr.workloads.hm_sg4_basis(8, 4, 4, 1, 2, scaleQ=np.linspace(0.8, 1.5, 8))
+    op = evr.ParamOp(basis, 1, evr.workloads.constant_keo_opgrids(8, 1, np.linspace(0.9, 1.2, 8), None))
+    _check(op, 2)
+    if os.environ.get("EVR_SG4_FORCE_GENERIC") != "1":
+        assert op.info(evr.lib.INFO_PATH) == 1 and op.info(evr.lib.INFO_ISO) == 0
