@@ -711,12 +711,18 @@ sg4_term_kernel_fast(const FastPlanDev P, const FastClassDev Cc, const int npsi,
             // once the last pass that reads the psi buffer is done, the sorted scatter map (4 B/entry) and the positions
             // (2 B/entry) of the term stream into that buffer while the remaining G -> B passes run
             const int nq32 = (nq + 31) & ~31;
+            const bool local_scatter = (P.dbg & 128) != 0 && nb0 == 1;
             auto stage_scatter_map = [&]() {
                 char *dst = reinterpret_cast<char *>(s_psi);
                 const char *sm = reinterpret_cast<const char *>(mp), *sp = reinterpret_cast<const char *>(pp);
                 const int c_map = nq32 >> 2, c_all = c_map + (nq32 >> 3);
-                for (int c = tid; c < c_all; c += gsize)
-                    cp_async16(dst + 16 * c, (c < c_map) ? sm + 16 * c : sp + 16 * (c - c_map));
+                if (local_scatter) {     // scatter in term-local order: the gather map is the scatter map, no positions
+                    const char *sg = reinterpret_cast<const char *>(gm);
+                    for (int c = tid; c < c_map; c += gsize) cp_async16(dst + 16 * c, sg + 16 * c);
+                } else {
+                    for (int c = tid; c < c_all; c += gsize)
+                        cp_async16(dst + 16 * c, (c < c_map) ? sm + 16 * c : sp + 16 * (c - c_map));
+                }
                 cp_async_commit();
             };
             if (G == 0) {
@@ -803,11 +809,11 @@ sg4_term_kernel_fast(const FastPlanDev P, const FastClassDev Cc, const int npsi,
                 // software-pipelined by hand (the entry of the next round is loaded before this round's reduction is
                 // issued); an unrolled loop would need the trip count, i.e. a division by the runtime group size
                 int j = tid;
-                int m = (j < nq32) ? s_map[j] : -1, q = (j < nq32) ? (int)s_pos[j] : 0;
+                int m = (j < nq32) ? s_map[j] : -1, q = (j < nq32) ? (local_scatter ? j : (int)s_pos[j]) : 0;
                 while (j < nq32) {
                     const int jn = j + gsize;
                     int mn = -1, qn = 0;
-                    if (jn < nq32) { mn = s_map[jn]; qn = s_pos[jn]; }
+                    if (jn < nq32) { mn = s_map[jn]; qn = local_scatter ? jn : (int)s_pos[jn]; }
                     if (m >= 0 && !nored) {
                         if (nb0 == 1) atomicAdd(y + m, weight * s_acc[q]);
                         else
