@@ -86,6 +86,17 @@ def ncu_traffic():
     return None
 
 
+def host_threads():
+    """Host threads for the CPU legs: every core this process may run on.  Not omp_get_max_threads(): torchrun exports
+    OMP_NUM_THREADS=1 to its workers, which would time the reference arm on ONE core at N > 1."""
+    if os.environ.get("EVR_CPU_THREADS"):
+        return max(1, int(os.environ["EVR_CPU_THREADS"]))
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def cpu_time_hpsi(op, psi, nthreads, budget_s=25.0):
     """Time the oracle port on a bounded sample of the workload; returns (seconds per full H|psi>, sample text)."""
     import numpy as np
@@ -149,7 +160,7 @@ def main():
         V = evr.workloads.henon_heiles_potential(basis)
         op = evr.ParamOp(basis, 1, evr.workloads.constant_keo_opgrids(args.D, 1, np.ones(args.D), V.reshape(-1, 1, 1)))
         psi = random_psi(basis.nb, args.npsi)
-        nth = sg4_oracle.max_threads()
+        nth = host_threads()
         from helpers import oracle_apply
         # bounded sample: the first terms holding ~1/16 of the grid points; one step = one pass over the sample
         csum = basis.tab_Sum_nq_OF_SRep
@@ -301,7 +312,7 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu:
         from oracle import sg4_oracle
         full = evr.ParamOp(basis, 1, ops) if (lo_, hi_) != (0, basis.nb_SG) else op
-        nth = sg4_oracle.max_threads()
+        nth = host_threads()
         sec, sample = cpu_time_hpsi(full, psi_h.numpy(), nth)
         cpu = {"value": 1.0 / sec, "unit": UNIT, "cores": nth, "kind": "port", "sample": sample}
 
