@@ -214,7 +214,7 @@ def main():
     psi_h = torch.from_numpy(random_psi(nvec, npsi)).pin_memory()
     out_h = torch.empty_like(psi_h).pin_memory()
     d_psi = psi_h.cuda(non_blocking=True)
-    d_out = torch.empty_like(d_psi)
+    d_out = tp.symmetric_empty(*d_psi.shape) if world > 1 else torch.empty_like(d_psi)   # peer-mapped when N > 1
     stream = torch.cuda.current_stream()
 
     def step():
@@ -225,6 +225,16 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    allreduce_check = None
+    if world > 1:       # the peer-memory reduction against NCCL on the same partial sums (rel. max difference, all ranks)
+        op.apply_device_ptr(npsi, d_psi.data_ptr(), d_out.data_ptr(), stream.cuda_stream)
+        ref = d_out.clone()
+        dist.all_reduce(ref, op=dist.ReduceOp.SUM)
+        tp.all_reduce(d_out)
+        chk = ((d_out - ref).abs().max() / ref.abs().max()).reshape(1)
+        dist.all_reduce(chk, op=dist.ReduceOp.MAX)
+        allreduce_check = float(chk[0])
+        assert allreduce_check < 1e-13, f"peer-memory all-reduce differs from NCCL: {allreduce_check:.3e}"
     for _ in range(args.warmup):
         step()
     barrier()
@@ -242,7 +252,7 @@ def main():
         op.apply_device_ptr(npsi, d_psi.data_ptr(), d_out.data_ptr(), stream.cuda_stream)
         kev[i][1].record(stream)
         if world > 1:
-            dist.all_reduce(d_out, op=dist.ReduceOp.SUM)
+            tp.all_reduce(d_out)
     ev1.record(stream)
     barrier()
     ms_total = ev0.elapsed_time(ev1)
@@ -283,12 +293,12 @@ def main():
     allreduce_ms = None
     if world > 1:                                               # the collective alone, for the scaling analysis
         for _ in range(3):
-            dist.all_reduce(d_out, op=dist.ReduceOp.SUM)
+            tp.all_reduce(d_out)
         barrier()
         a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a0.record(stream)
         for _ in range(args.steps):
-            dist.all_reduce(d_out, op=dist.ReduceOp.SUM)
+            tp.all_reduce(d_out)
         a1.record(stream)
         barrier()
         ta = torch.tensor([a0.elapsed_time(a1) / args.steps], dtype=torch.float64, device="cuda")
@@ -321,11 +331,12 @@ def main():
                 "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
                 "data": "synthetic",
                 "config": {"workload": workload_name(args.D, args.L, npsi), "nb_SG": basis.nb_SG, "grid_points": basis.nqq,
-                           "nb": basis.nb, "npsi": npsi, "parallelism": f"terms/{world} ({args.partition}-balanced contiguous ranges) + NCCL allreduce" if world > 1 else "1 GPU",
+                           "nb": basis.nb, "npsi": npsi, "parallelism": f"terms/{world} ({args.partition}-balanced contiguous ranges) + all-reduce: {tp.collective}" if world > 1 else "1 GPU",
                            "cache": "operator grid + mapping streamed per step (%.0f MB) > L2; no flush needed" % (alg1 / 1e6)
                            if alg1 > 130e6 else "inputs smaller than L2 (L2-warm numbers)",
                            "kernel_path": int(op.info(evr.lib.INFO_PATH)), "iso_flavour": int(op.info(evr.lib.INFO_ISO)), "setup_s": round(t_setup, 2)},
-                "e2e": e2e, "allreduce_ms": allreduce_ms, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks}
+                "e2e": e2e, "allreduce_ms": allreduce_ms, "allreduce_vs_nccl_rel_diff": allreduce_check,
+                "gpu_launches": int(launches) + (args.steps if (world > 1 and tp._symm) else 0), "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -4,7 +4,10 @@ ranges, replicated packed psi, partial results summed with an all-reduce.
 This is the reference's MPI "scheme 1" (Action_MPI_S1, sub_Operator/sub_OpPsi_SG4_MPI.f90:454-571):
 rank r applies the terms iGs_MPI(1:2,r) (ini_iGs_MPI, sub_Basis_SG4/sub_module_basis_BtoG_GtoB_SG4_MPI.f90:
 639-669) into a zeroed vector, then MPI_Reduce_sum_Bcast (= all-reduce) over size_RvecB*size_psi doubles.
-Here the collective is torch.distributed (NCCL over NVLink on GPUs, gloo in the CPU tests).
+Here the collective is, on GPUs of one node, the library's own peer-memory kernel (evr_sg4_allreduce_slices,
+include/evr_sg4_comm.h: every rank sums one slice of all ranks' buffers over NVLink and stores it back into all of
+them) on buffers from ``TermParallelOp.symmetric_empty``; for any other buffer it is torch.distributed's all_reduce
+(NCCL on GPUs, gloo in the CPU tests).
 """
 from __future__ import annotations
 
@@ -46,6 +49,56 @@ class TermParallelOp:
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self._local = local_apply or self._cuda_apply
+        self._symm = {}            # data_ptr -> (tensor, symmetric-memory handle, ctypes array of peer pointers)
+        self.collective = "torch.distributed.all_reduce"
+
+    def symmetric_empty(self, *shape):
+        """float64 CUDA tensor that every rank of the node has mapped (torch.distributed._symmetric_memory); ``apply`` /
+        ``all_reduce`` on it use the peer-memory kernel.  Collective call.  Falls back to an ordinary tensor (and the
+        NCCL all-reduce) when symmetric memory is unavailable on ANY rank, or with EVR_SG4_ALLREDUCE=nccl."""
+        import os
+        import torch
+        import torch.distributed as dist
+        dev = torch.device("cuda", torch.cuda.current_device())
+        ok, t, hdl = 0, None, None
+        if self.world > 1 and os.environ.get("EVR_SG4_ALLREDUCE", "p2p") != "nccl" and self.world <= 16:
+            try:
+                import torch.distributed._symmetric_memory as symm_mem
+                grp = self.group if self.group is not None else dist.group.WORLD
+                t = symm_mem.empty(*shape, dtype=torch.float64, device=dev)
+                hdl = symm_mem.rendezvous(t, grp)
+                ok = 1 if (hdl.world_size == self.world and hdl.rank == self.rank and t.data_ptr() % 16 == 0) else 0
+            except Exception as e:      # noqa: BLE001 - any failure means "use NCCL", agreed on by all ranks below
+                self._symm_error = repr(e)
+                ok = 0
+        if self.world > 1:
+            flag = torch.tensor([ok], dtype=torch.int32, device=dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
+            ok = int(flag.item())
+        if not ok:
+            return torch.empty(*shape, dtype=torch.float64, device=dev)
+        ptrs = (C.c_void_p * self.world)(*[int(p) for p in hdl.buffer_ptrs])
+        self._symm[t.data_ptr()] = (t, hdl, ptrs)
+        self.collective = "evr_sg4_allreduce_slices (NVLink peer memory, reduce-scatter + all-gather in one kernel)"
+        return t
+
+    def all_reduce(self, out):
+        """In-place sum of ``out`` over the ranks (MPI_Reduce_sum_Bcast of Action_MPI_S1)."""
+        if self.world == 1:
+            return out
+        ent = self._symm.get(out.data_ptr()) if out.is_cuda else None
+        if ent is None:
+            import torch.distributed as dist
+            dist.all_reduce(out, op=dist.ReduceOp.SUM, group=self.group)
+            return out
+        import torch
+        _, hdl, ptrs = ent
+        hdl.barrier(channel=0)      # every rank's partial sum is complete (stream-ordered, device-side)
+        _lib.check(_lib.lib().evr_sg4_allreduce_slices(ptrs, self.world, self.rank, out.numel(),
+                                                       C.c_void_p(torch.cuda.current_stream().cuda_stream)),
+                   "evr_sg4_allreduce_slices")
+        hdl.barrier(channel=1)      # every slice has been written everywhere
+        return out
 
     def _cuda_apply(self, psi, out):
         import torch
@@ -56,7 +109,4 @@ class TermParallelOp:
     def apply(self, psi, out):
         """out <- sum over ranks of (H restricted to the rank's terms) psi ; psi replicated on every rank."""
         self._local(psi, out)
-        if self.world > 1:
-            import torch.distributed as dist
-            dist.all_reduce(out, op=dist.ReduceOp.SUM, group=self.group)
-        return out
+        return self.all_reduce(out)

@@ -26,6 +26,7 @@ EXPORTS = [
     "evr_sg4_ini_iGs", "evr_sg4_balanced_iGs",
     "evr_sg4_plan_create", "evr_sg4_plan_set_op", "evr_sg4_plan_set_op10", "evr_sg4_apply", "evr_sg4_apply_device", "evr_sg4_apply_device_scaled",
     "evr_sg4_plan_info", "evr_sg4_plan_destroy",
+    "evr_sg4_allreduce_slices",
 ]
 
 
@@ -86,6 +87,8 @@ def lib():
     L.evr_sg4_plan_info.argtypes = [vp, i32]
     L.evr_sg4_plan_destroy.restype = i32
     L.evr_sg4_plan_destroy.argtypes = [C.POINTER(vp)]
+    L.evr_sg4_allreduce_slices.restype = i32
+    L.evr_sg4_allreduce_slices.argtypes = [vp, i32, i32, i64, vp]
     _lib = L
     return L
 

@@ -381,3 +381,25 @@ def test_fast_path_with_matrix_pool_in_global_memory(evr):
     _check(op, 2)
     if os.environ.get("EVR_SG4_FORCE_GENERIC") != "1":
         assert op.info(evr.lib.INFO_PATH) == 1 and op.info(evr.lib.INFO_ISO) == 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("np_,n", [(2, 1001), (3, 4096), (8, 12345), (1, 7), (4, 2)])
+def test_peer_memory_allreduce_kernel_single_device(evr, np_, n):
+    """evr_sg4_allreduce_slices (include/evr_sg4_comm.h) with all "ranks" on one device: after every rank's call all
+    buffers hold the sum in the fixed order 0..np-1, bit-identical (odd lengths, slices smaller than a vector unit)."""
+    import ctypes as C
+    import torch
+    torch.manual_seed(n)
+    bufs = [torch.randn(n, dtype=torch.float64, device="cuda") for _ in range(np_)]
+    want = bufs[0].clone()
+    for b in bufs[1:]:
+        want = want + b
+    ptrs = (C.c_void_p * np_)(*[b.data_ptr() for b in bufs])
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    for r in range(np_):
+        evr.lib.check(evr.lib.lib().evr_sg4_allreduce_slices(ptrs, np_, r, n, st), "allreduce")
+    torch.cuda.synchronize()
+    for b in bufs:
+        assert torch.equal(b, want)
+    assert evr.lib.lib().evr_sg4_allreduce_slices(ptrs, 0, 0, n, st) != 0      # bad arguments fail loudly
