@@ -37,6 +37,10 @@ def _worker(rank, world, port, q):
         tp.apply(psi, out)
         ref = oracle_apply(op_full, psi.numpy())
         err = float(np.abs(out.numpy() - ref).max() / np.abs(ref).max())
+        # host buffers are never peer-mapped: the collective must be torch.distributed's, and all_reduce() alone sums in place
+        assert tp.collective == "torch.distributed.all_reduce" and not tp._symm
+        ones = torch.full((5,), float(rank + 1), dtype=torch.float64)
+        assert torch.equal(tp.all_reduce(ones), torch.full((5,), 3.0, dtype=torch.float64))
         q.put((rank, lo, hi, err))
     finally:
         dist.destroy_process_group()
