@@ -98,35 +98,22 @@ def host_threads():
 
 
 def cpu_time_hpsi(op, psi, nthreads, budget_s=25.0):
-    """Time the oracle port on a bounded sample of the workload; returns (seconds per full H|psi>, sample text)."""
+    """Time the oracle port on the full workload when it fits the budget, else on a bounded sample.
+    Returns (seconds per full H|psi>, sample text, full oracle result or None)."""
     import numpy as np
     from helpers import oracle_apply
     b = op.BasisnD
-    csum = b.tab_Sum_nq_OF_SRep
-    frac = 1.0 / 16.0
-    hi = int(np.searchsorted(csum, frac * b.nqq)) + 1
-    hi = min(max(hi, 1), b.nb_SG)
     t0 = time.perf_counter()
-    oracle_apply(op, psi, nthreads=nthreads, iG_range=(0, hi))
-    t = time.perf_counter() - t0
-    pts = int(csum[hi - 1])
-    est_full = t * b.nqq / pts
-    if est_full * 3 <= budget_s:
-        ts = []
-        for _ in range(3):
-            t0 = time.perf_counter()
-            oracle_apply(op, psi, nthreads=nthreads)
-            ts.append(time.perf_counter() - t0)
-        return sorted(ts)[1], f"3 full H|psi> (all {b.nb_SG} terms, {b.nqq} grid points), median"
-    reps = max(1, int(budget_s / max(t, 1e-3)) - 1)
-    ts = [t]
-    for _ in range(min(reps, 2)):
+    ref = oracle_apply(op, psi, nthreads=nthreads)          # also the parity reference of this run
+    t_first = time.perf_counter() - t0
+    reps = int(min(4, max(0, (budget_s - t_first) // max(t_first, 1e-3))))
+    ts = [t_first]
+    for _ in range(reps):
         t0 = time.perf_counter()
-        oracle_apply(op, psi, nthreads=nthreads, iG_range=(0, hi))
+        oracle_apply(op, psi, nthreads=nthreads)
         ts.append(time.perf_counter() - t0)
     tm = sorted(ts)[len(ts) // 2]
-    return tm * b.nqq / pts, (f"terms 1..{hi} of {b.nb_SG} ({pts} of {b.nqq} grid points, {len(ts)} runs, median), "
-                              f"scaled by grid points to one full H|psi>")
+    return tm, f"{len(ts)} full H|psi> (all {b.nb_SG} terms, {b.nqq} grid points), median", ref
 
 
 def main():
@@ -162,19 +149,16 @@ def main():
         psi = random_psi(basis.nb, args.npsi)
         nth = host_threads()
         from helpers import oracle_apply
-        # bounded sample: the first terms holding ~1/16 of the grid points; one step = one pass over the sample
-        csum = basis.tab_Sum_nq_OF_SRep
-        hi = min(max(int(np.searchsorted(csum, basis.nqq / 16.0)) + 1, 1), basis.nb_SG)
-        pts = int(csum[hi - 1])
+        # one step = one full H|psi> of the workload (all terms): ~0.2-0.3 s on 16 host threads at L=7, so no sampling
+        # (a sample of the first terms under-weights the large terms and biases the CPU arm low)
         per = []
         for i in range(args.warmup + args.steps):
             t0 = time.perf_counter()
-            oracle_apply(op, psi, nthreads=nth, iG_range=(0, hi))
+            oracle_apply(op, psi, nthreads=nth)
             if i >= args.warmup:
                 per.append(time.perf_counter() - t0)
-        sec = (sum(per) / len(per)) * basis.nqq / pts
-        sample = (f"each step = terms 1..{hi} of {basis.nb_SG} ({pts} of {basis.nqq} grid points), "
-                  f"scaled by grid points to one full H|psi>")
+        sec = sum(per) / len(per)
+        sample = f"each step = one full H|psi> (all {basis.nb_SG} terms, {basis.nqq} grid points); mean of {len(per)} steps"
         val = 1.0 / sec
         line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "strong",
@@ -313,18 +297,30 @@ def main():
     achieved = alg / (k_ms * 1e-3) / 1e9
     traffic = ncu_traffic()
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": (traffic or {}).get("dram_bytes_per_launch"), "peak_source": peak_src,
+                # ncu figure of the single-GPU launch (profiles/traffic.json); not measured for a term sub-range
+                "traffic": (traffic or {}).get("dram_bytes_per_launch") if world == 1 else None, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg, "kernel_ms": k_ms,
                 "kernel": "sg4_term_kernel_fast (permute-in + memset of Hpsi + one launch per term-size class + permute-out, per H|psi>)",
                 "flops_per_launch": op.info(evr.lib.INFO_FLOPS_NPSI1) * npsi}
 
-    cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu:
-        from oracle import sg4_oracle
-        full = evr.ParamOp(basis, 1, ops) if (lo_, hi_) != (0, basis.nb_SG) else op
-        nth = host_threads()
-        sec, sample = cpu_time_hpsi(full, psi_h.numpy(), nth)
-        cpu = {"value": 1.0 / sec, "unit": UNIT, "cores": nth, "kind": "port", "sample": sample}
+    # ---- parity of THIS run's device result (after the all-reduce when N > 1) against the CPU oracle on the same psi,
+    # and the CPU baseline (the same oracle calls, timed; N = 1 only)
+    cpu, parity = None, None
+    if not args.no_cpu:
+        tp.apply(d_psi, d_out)
+        torch.cuda.synchronize()
+        got = d_out.cpu().numpy()
+        if rank == 0:
+            from oracle import sg4_oracle
+            full = evr.ParamOp(basis, 1, ops) if (lo_, hi_) != (0, basis.nb_SG) else op
+            nth = host_threads()
+            sec, sample, ref = cpu_time_hpsi(full, psi_h.numpy(), nth, budget_s=25.0 if world == 1 else 0.0)
+            from helpers import rel_l2
+            errs = [rel_l2(got[i], ref[i]) for i in range(npsi)]
+            parity = {"rel_l2": max(errs), "tol": 1e-12, "against": "oracle port (oracle/sg4_oracle.c), same psi, full workload",
+                      "n_gpus": world, "ok": bool(max(errs) <= 1e-12)}
+            if world == 1:
+                cpu = {"value": 1.0 / sec, "unit": UNIT, "cores": nth, "kind": "port", "sample": sample}
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -336,8 +332,11 @@ def main():
                            if alg1 > 130e6 else "inputs smaller than L2 (L2-warm numbers)",
                            "kernel_path": int(op.info(evr.lib.INFO_PATH)), "iso_flavour": int(op.info(evr.lib.INFO_ISO)), "setup_s": round(t_setup, 2)},
                 "e2e": e2e, "allreduce_ms": allreduce_ms, "allreduce_vs_nccl_rel_diff": allreduce_check,
-                "gpu_launches": int(launches) + (args.steps if (world > 1 and tp._symm) else 0), "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks}
+                "gpu_launches": int(launches) + (args.steps if (world > 1 and tp._symm) else 0), "roofline": roofline, "cpu_baseline": cpu, "parity": parity, "clocks": clocks}
         print(json.dumps(line))
+        if parity is not None and not parity["ok"]:
+            print(f"PARITY FAILURE: rel L2 vs oracle = {parity['rel_l2']:.3e} > 1e-12", file=sys.stderr)
+            return 1
     if world > 1:
         dist.destroy_process_group()
     return 0

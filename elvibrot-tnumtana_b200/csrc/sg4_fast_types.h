@@ -8,6 +8,7 @@
 namespace evr {
 
 #define EVR_MAXG 8          // max groups (<= 16 active modes) per term on the fast path
+#define EVR_MAX_FCLASSES 16 // (size class, kernel flavour) pairs = launches per H|psi> on the fast path
 #define EVR_RT_NMAX 16      // runtime-size single-mode tiles keep up to 16 values in registers
 
 struct FastGroup {

@@ -76,11 +76,12 @@ struct evr_sg4_plan {
     bool fast_iso = false;                  // constant-matrix instantiation (sg4_iso.cu)
     std::vector<double> iso_blocks;         // its [B|BTw|T] blocks, bound to the __constant__ array before each launch
     int iso_id = 0;
-    evr::FastClassDev fclass[13];
-    size_t fclass_smem[13] = {0};
-    int fclass_ctas[13] = {0};
-    bool fclass_is_iso[13] = {false};
-    int fclass_flavour[13] = {0};        // 0 templated, 1 runtime-size, 2 cube tiles (plain) / iso with large tiles, 3 iso
+    int n_fitems = 0;                       // work items (batches of same-schedule terms) of the fast path
+    evr::FastClassDev fclass[EVR_MAX_FCLASSES];
+    size_t fclass_smem[EVR_MAX_FCLASSES] = {0};
+    int fclass_ctas[EVR_MAX_FCLASSES] = {0};
+    bool fclass_is_iso[EVR_MAX_FCLASSES] = {false};
+    int fclass_flavour[EVR_MAX_FCLASSES] = {0};        // 0 templated, 1 runtime-size, 2 cube tiles (plain) / iso with large tiles, 3 iso
     // device
     evr::TermDev *d_terms = nullptr;
     uint8_t *d_lev = nullptr;
@@ -97,8 +98,8 @@ struct evr_sg4_plan {
     int ctas10_max = 0;
     int64_t stage_cap = 0;
     cudaStream_t stream = nullptr;
-    cudaStream_t side[13] = {nullptr};   // class kernels overlap their tails
-    cudaEvent_t ev_fork = nullptr, ev_join[13] = {nullptr};
+    cudaStream_t side[EVR_MAX_FCLASSES] = {nullptr};   // class kernels overlap their tails
+    cudaEvent_t ev_fork = nullptr, ev_join[EVR_MAX_FCLASSES] = {nullptr};
     size_t smem_bytes = 0;
     int grid_ctas = 0, gen_ctas_max = 0;
     // generic kernel: one launch per term-size class (CTA of 256/128/64/32 threads)
@@ -312,7 +313,7 @@ extern "C" int evr_sg4_plan_create(evr_sg4_plan **out, int device,
     }
     if (!getenv("EVR_SG4_SINGLE_STREAM")) {
         bool ok_ev = cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming) == cudaSuccess;
-        for (int c = 1; c < 13 && ok_ev; ++c)
+        for (int c = 1; c < EVR_MAX_FCLASSES && ok_ev; ++c)
             ok_ev = cudaStreamCreateWithFlags(&p->side[c], cudaStreamNonBlocking) == cudaSuccess &&
                     cudaEventCreateWithFlags(&p->ev_join[c], cudaEventDisableTiming) == cudaSuccess;
         if (!ok_ev) { evr_sg4_plan_destroy(&p); return fail("evr_sg4_plan_create: side stream/event creation failed"); }
@@ -452,12 +453,11 @@ static int build_fast_path(evr_sg4_plan *p, int nb_Term, const int32_t *term_mod
             if (n > 1 && fast_template_id(n, 0) == 0) { term_rt[t] = 1; if (n > EVR_RT_NMAX) return 0; }
         }
     }
-    // size classes and threads per term (tunable for experiments: EVR_SG4_T0/T1 thresholds, EVR_SG4_G0/G1/G2 group sizes)
+    // ---- tunables (experiments: environment overrides) ---------------------------------------------------------
     auto envi = [](const char *n, int d) { const char *v = getenv(n); return v ? atoi(v) : d; };
-    const int64_t thr0 = envi("EVR_SG4_T0", iso ? 700 : 1024), thr1 = envi("EVR_SG4_T1", 384), thrA = envi("EVR_SG4_TA", 2000);
     // cube tiles (three equal modes of size 3 or 2 per thread): how many cubes minimise the group count of a term
     const bool use_cubes = iso_big || (!iso && envi("EVR_SG4_CUBES", 0) != 0);
-    auto n_cubes = [](int c) { return (c == 3 || c == 5 || c == 6) ? c / 3 : (c >= 7 ? (c - 4) / 3 + ((c - 4) % 3 == 2 ? 0 : 0) + 1 : 0); };
+    auto n_cubes = [](int c) { return (c == 3 || c == 5 || c == 6) ? c / 3 : (c >= 7 ? (c - 4) / 3 + 1 : 0); };
     std::vector<char> term_tri(p->n_terms, 0);
     if (use_cubes)
         for (int t = 0; t < p->n_terms; ++t) {
@@ -470,32 +470,19 @@ static int build_fast_path(evr_sg4_plan *p, int nb_Term, const int32_t *term_mod
             }
             if (iso_big || n_cubes(c3) > 0 || n_cubes(c2) > 0) term_tri[t] = 1;   // iso with large tiles: every term runs in the cube-capable instantiation
         }
-    auto class_of = [&](int t) {
-        const int64_t sz = (int64_t)p->h_tab_nq[p->iG_begin + t] * nb0;
-        // iso (768-thread) flavour: a fourth size class for the very largest terms, so that the shared-memory buffers of the
-        // next class are sized for e.g. 1215 instead of 2187 points and almost twice as many of its terms are in flight per SM
-        if (term_iso[t] && !term_tri[t] && sz > thrA) return 12;
-        return (sz > thr0 ? 0 : (sz > thr1 ? 1 : 2)) + (term_rt[t] ? 3 : (term_tri[t] ? 6 : (term_iso[t] ? 9 : 0)));
-    };
-    const int class_gsize[13] = {envi("EVR_SG4_G0", 128), envi("EVR_SG4_G1", 64), envi("EVR_SG4_G2", 32),
-                                 envi("EVR_SG4_G0", 128), envi("EVR_SG4_G1", 64), envi("EVR_SG4_G2", 32),
-                                 envi("EVR_SG4_G0T", 64), envi("EVR_SG4_G1T", 32), envi("EVR_SG4_G2T", 32),
-                                 envi("EVR_SG4_G0", 64), envi("EVR_SG4_G1", 32), envi("EVR_SG4_G2", 32), envi("EVR_SG4_GA", 128)};
-    std::vector<int> forder(p->n_terms);
-    std::iota(forder.begin(), forder.end(), 0);
-    std::stable_sort(forder.begin(), forder.end(), [&](int a, int b) {
-        const int ca = class_of(a) % 12, cb = class_of(b) % 12;   // class 12 (largest iso terms) is launched first
-        if (class_of(a) != class_of(b)) return (ca != cb) ? ca < cb : class_of(a) > class_of(b);
-        return p->h_cost[a] > p->h_cost[b];
-    });
+    // flavour = which instantiation of the kernel runs a term:
+    //   0 templated tiles, matrices from the pool | 1 runtime-size tiles | 2 cube tiles (512 threads) | 3 iso (768 threads)
+    auto flavour_of = [&](int t) { return term_rt[t] ? 1 : (term_tri[t] ? 2 : (term_iso[t] ? 3 : 0)); };
     // ---- internal order of the packed vector: functions reached by exactly the same set of Smolyak terms
     // (= same level vector) are stored contiguously, so that every term reads/updates whole blocks and the
     // gather/scatter of a warp touches a few contiguous runs instead of 32 separate sectors.
     // The membership signature is a sum of per-term 64-bit hashes; no multi-index table is needed.
     // The two permutation kernels cost ~12 us per H|psi>, so small problems keep the caller's order (identity
     // permutation, term entries still sorted by address); EVR_SG4_BLOCK_ORDER=0/1 overrides the size heuristic.
+    // The heuristic keys on the size of the WHOLE Smolyak grid, so that every rank of a term-parallel run uses the
+    // same layout as the single-GPU plan.
     std::vector<int32_t> inv_perm((size_t)p->nb), perm((size_t)p->nb);
-    bool block_order = p->NQ_local >= 8000000;
+    bool block_order = p->NQ_total >= 8000000;
     if (getenv("EVR_SG4_BLOCK_ORDER")) block_order = atoi(getenv("EVR_SG4_BLOCK_ORDER")) != 0;
     p->fast_block_order = block_order;
     if (!block_order) {
@@ -514,28 +501,18 @@ static int build_fast_path(evr_sg4_plan *p, int nb_Term, const int32_t *term_mod
         std::stable_sort(perm.begin(), perm.end(), [&](int32_t a, int32_t b) { return sig[a] < sig[b]; });
         for (int64_t i = 0; i < p->nb; ++i) inv_perm[perm[i]] = (int32_t)i;
     }
-    std::vector<evr::FastTermDev> fterms(p->n_terms);
-    // Per-term slices of the fast-path arrays are padded to 32 entries (aligned 128-bit loads, no tail guards):
-    //   gmap : packed index of every term-local entry in the INTERNAL term layout (gather: vector loads, linear stores)
-    //   fmap : the same indices sorted ascending + fpos = their term-local positions (scatter: neighbouring lanes hit
-    //          neighbouring addresses, so the FP64 reductions of a warp share L2 sectors)
-    //   fV   : V in the internal term layout
-    // padding entries: index -1 (skipped), position 0, V = 0.
-    std::vector<int64_t> pad_off(p->n_terms + 1, 0);
-    for (int t = 0; t < p->n_terms; ++t) pad_off[t + 1] = pad_off[t] + (((int64_t)p->h_tab_nq[p->iG_begin + t] + 31) & ~(int64_t)31);
-    const int64_t NQ_pad = std::max<int64_t>(pad_off[p->n_terms], 32);
-    std::vector<int32_t> fmap((size_t)NQ_pad, -1), gmap((size_t)NQ_pad, -1);
-    std::vector<uint16_t> fpos((size_t)NQ_pad, 0);
-    std::vector<double> fV;
-    if (Vgrid) fV.assign((size_t)nb0 * nb0 * NQ_pad, 0.0);
-    bool ok = true;
+    // ---- per-term schedule: active modes -> register-tile groups, internal (permuted) term layout ---------------
+    struct TermSched {
+        evr::FastTermDev F;                     // nq = points of ONE term; offsets filled per batch below
+        std::vector<int> in_n, in_ref;          // per internal mode: size, stride in the reference term layout
+    };
+    std::vector<TermSched> sched(p->n_terms);
+    int ok = 1;
 #pragma omp parallel for schedule(dynamic, 64)
-    for (int w = 0; w < p->n_terms; ++w) {
-        if (!ok) continue;
-        const int t = forder[w], iG = p->iG_begin + t;
-        evr::FastTermDev &F = fterms[w];
+    for (int t = 0; t < p->n_terms; ++t) {
+        const int iG = p->iG_begin + t;
+        evr::FastTermDev &F = sched[t].F;
         std::memset(&F, 0, sizeof(F));
-        F.map_off = pad_off[t]; F.grid_off = pad_off[t];
         F.nq = p->h_tab_nq[iG];
         double wgt = p->h_weight[iG], shift = c00;
         // active modes (size > 1), sorted by size
@@ -605,11 +582,15 @@ static int build_fast_path(evr_sg4_plan *p, int nb_Term, const int32_t *term_mod
         }
         auto gsize = [&](const Grp &g) { return act[g.a1].n * (g.a2 >= 0 ? act[g.a2].n : 1) * (g.a3 >= 0 ? act[g.a3].n : 1); };
         std::stable_sort(grp.begin(), grp.end(), [&](const Grp &a, const Grp &b) { return gsize(a) > gsize(b); });
-        if ((int)grp.size() > EVR_MAXG) { ok = false; continue; }
+        if ((int)grp.size() > EVR_MAXG) {
+#pragma omp atomic write
+            ok = 0;
+            continue;
+        }
         F.ngroups = (int)grp.size();
         F.weight = wgt; F.vshift = shift;
         // internal mode order and strides
-        std::vector<int> in_n, in_ref;          // per internal mode: size, reference stride
+        std::vector<int> &in_n = sched[t].in_n, &in_ref = sched[t].in_ref;
         int stride = 1;
         for (size_t g = 0; g < grp.size(); ++g) {
             const Act &A1 = act[grp[g].a1];
@@ -639,31 +620,120 @@ static int build_fast_path(evr_sg4_plan *p, int nb_Term, const int32_t *term_mod
                 stride *= A3.n;
             }
             Gd.tmpl = term_rt[t] ? 0 : (Gd.n3 == 3 ? EVR_TMPL_CUBE3 : (Gd.n3 == 2 ? EVR_TMPL_CUBE2 : (unsigned short)fast_template_id(Gd.n1, Gd.n2, term_iso[t] != 0)));
-            if (!term_rt[t] && Gd.tmpl == 0) ok = false;
+            if (!term_rt[t] && Gd.tmpl == 0) {
+#pragma omp atomic write
+                ok = 0;
+            }
         }
-        // permutation: internal index q' -> reference index q (odometer over internal modes)
-        const int nm = (int)in_n.size();
-        std::vector<int> idx(nm, 0);
-        int64_t q = 0;
-        const int32_t *msrc = p->h_map.data() + p->h_map_off[t];
+    }
+    if (!ok) return 0;
+    // ---- batches ("super-terms"): Smolyak terms with the SAME schedule (tile groups, matrices, folded weight and
+    // shift) are processed together as one work item.  In the internal layout the term index is simply one more (slowest)
+    // dimension, so every pass runs over all tiles of all terms of the batch with full warps, one barrier per pass and one
+    // descriptor, and the batch's map / V slices are contiguous.  Every term of a shape qualifies when the modes of equal
+    // size share their 1-D basis (iso flavour: the kernel ignores the matrix offsets); otherwise only terms on modes with
+    // identical matrices do.  The batch capacity adapts to the problem size so that small grids still fill the GPU.
+    auto term_is_iso = [&](int t) { const int fl = flavour_of(t); return iso && (fl == 3 || (fl == 2 && iso_big)); };
+    const int64_t bcap_max = std::max(1, envi("EVR_SG4_BCAP", 4700));                   // doubles per psi/acc buffer
+    const int64_t target_items = (int64_t)p->sm_count * std::max(1, envi("EVR_SG4_ITEMS_PER_SM", 16));
+    const int64_t bcap = std::max<int64_t>(1, std::min<int64_t>(bcap_max, (p->NQ_local * nb0 + target_items - 1) / target_items));
+    struct Batch { std::vector<int> terms; int flavour, szclass; int64_t size; double cost; };
+    std::vector<Batch> batches;
+    const int64_t th0 = envi("EVR_SG4_TH0", 3000), th1 = envi("EVR_SG4_TH1", 1400), th2 = envi("EVR_SG4_TH2", 600);
+    {
+        std::map<std::string, std::vector<int>> by_key;
+        for (int t = 0; t < p->n_terms; ++t) {
+            const evr::FastTermDev &F = sched[t].F;
+            std::string k;
+            auto put = [&](const void *ptr, size_t n) { k.append(reinterpret_cast<const char *>(ptr), n); };
+            const int fl = flavour_of(t);
+            put(&fl, sizeof fl); put(&F.nq, sizeof F.nq); put(&F.ngroups, sizeof F.ngroups);
+            put(&F.weight, sizeof F.weight); put(&F.vshift, sizeof F.vshift);
+            for (int g = 0; g < F.ngroups; ++g) {
+                evr::FastGroup Gd = F.g[g];
+                if (term_is_iso(t)) Gd.mat1 = Gd.mat2 = Gd.mat3 = 0;
+                put(&Gd, sizeof Gd);
+            }
+            by_key[k].push_back(t);
+        }
+        for (auto &kv : by_key) {
+            const std::vector<int> &tl = kv.second;
+            const evr::FastTermDev &F0 = sched[tl[0]].F;
+            const int64_t tsz = (int64_t)F0.nq * nb0;
+            int64_t T = (F0.ngroups == 0) ? 1 : std::max<int64_t>(1, bcap / tsz);
+            if (envi("EVR_SG4_BATCH", 1) == 0) T = 1;
+            const int64_t n = (int64_t)tl.size(), nbat = (n + T - 1) / T;
+            for (int64_t b = 0; b < nbat; ++b) {                 // near-equal batches (sizes differ by at most one term)
+                const int64_t lo = b * n / nbat, hi = (b + 1) * n / nbat;
+                Batch Bt;
+                Bt.terms.assign(tl.begin() + lo, tl.begin() + hi);
+                Bt.flavour = flavour_of(tl[0]);
+                Bt.size = tsz * (hi - lo);
+                Bt.szclass = Bt.size > th0 ? 0 : (Bt.size > th1 ? 1 : (Bt.size > th2 ? 2 : 3));
+                Bt.cost = 0.0;
+                for (int64_t j = lo; j < hi; ++j) Bt.cost += p->h_cost[tl[j]];
+                batches.push_back(std::move(Bt));
+            }
+        }
+    }
+    // work order: size class (largest items first), then flavour, then cost descending
+    std::stable_sort(batches.begin(), batches.end(), [](const Batch &a, const Batch &b) {
+        if (a.szclass != b.szclass) return a.szclass < b.szclass;
+        if (a.flavour != b.flavour) return a.flavour > b.flavour;
+        return a.cost > b.cost;
+    });
+    const int n_items = (int)batches.size();
+    std::vector<evr::FastTermDev> fterms(n_items);
+    // Per-item slices of the fast-path arrays are padded to 32 entries (aligned 128-bit copies, no tail guards):
+    //   gmap : packed index of every entry of the batch in the INTERNAL layout (gather: vector loads, linear stores)
+    //   fmap : the same indices sorted ascending + fpos = their positions in the batch buffer (scatter: neighbouring
+    //          lanes hit neighbouring addresses, so the FP64 reductions of a warp share L2 sectors)
+    //   fV   : V in the internal layout
+    // padding entries: index -1 (skipped), position 0, V = 0.
+    std::vector<int64_t> pad_off(n_items + 1, 0);
+    for (int w = 0; w < n_items; ++w) {
+        if (batches[w].size / nb0 > 65535) return 0;          // positions are 16-bit
+        pad_off[w + 1] = pad_off[w] + ((batches[w].size / nb0 + 31) & ~(int64_t)31);
+    }
+    const int64_t NQ_pad = std::max<int64_t>(pad_off[n_items], 32);
+    std::vector<int32_t> fmap((size_t)NQ_pad, -1), gmap((size_t)NQ_pad, -1);
+    std::vector<uint16_t> fpos((size_t)NQ_pad, 0);
+    std::vector<double> fV;
+    if (Vgrid) fV.assign((size_t)nb0 * nb0 * NQ_pad, 0.0);
+#pragma omp parallel for schedule(dynamic, 8)
+    for (int w = 0; w < n_items; ++w) {
+        const Batch &Bt = batches[w];
+        evr::FastTermDev &F = fterms[w];
+        F = sched[Bt.terms[0]].F;
+        const int nq1 = F.nq, T = (int)Bt.terms.size();
+        F.nq = nq1 * T;
+        F.map_off = pad_off[w]; F.grid_off = pad_off[w];
         int32_t *mdst = fmap.data() + F.map_off;
         int32_t *gdst = gmap.data() + F.map_off;
         uint16_t *pdst = fpos.data() + F.map_off;
-        const int64_t ref_grid_off = p->h_grid_off[t];
-        if (F.nq > 65535) { ok = false; continue; }
         std::vector<std::pair<int32_t, uint16_t>> ent((size_t)F.nq);
-        for (int qp = 0; qp < F.nq; ++qp) {
-            const int32_t m = msrc[q];
-            ent[qp] = { m > 0 ? inv_perm[m - 1] : INT32_MAX, (uint16_t)qp };
-            gdst[qp] = m > 0 ? inv_perm[m - 1] : -1;
-            if (Vgrid)
-                for (int ij = 0; ij < nb0 * nb0; ++ij)
-                    fV[(size_t)ij * NQ_pad + F.grid_off + qp] = Vgrid[(size_t)ij * p->NQ_total + p->grid_start + ref_grid_off + q];
-            for (int m2 = 0; m2 < nm; ++m2) {
-                q += in_ref[m2];
-                if (++idx[m2] < in_n[m2]) break;
-                q -= (int64_t)in_ref[m2] * in_n[m2];
-                idx[m2] = 0;
+        for (int j = 0; j < T; ++j) {
+            const int t = Bt.terms[j];
+            const TermSched &S = sched[t];
+            // permutation: internal index q' -> reference index q (odometer over internal modes)
+            const int nm = (int)S.in_n.size();
+            std::vector<int> idx(nm, 0);
+            int64_t q = 0;
+            const int32_t *msrc = p->h_map.data() + p->h_map_off[t];
+            const int64_t ref_grid_off = p->h_grid_off[t];
+            for (int qp = j * nq1; qp < (j + 1) * nq1; ++qp) {
+                const int32_t m = msrc[q];
+                ent[qp] = { m > 0 ? inv_perm[m - 1] : INT32_MAX, (uint16_t)qp };
+                gdst[qp] = m > 0 ? inv_perm[m - 1] : -1;
+                if (Vgrid)
+                    for (int ij = 0; ij < nb0 * nb0; ++ij)
+                        fV[(size_t)ij * NQ_pad + F.grid_off + qp] = Vgrid[(size_t)ij * p->NQ_total + p->grid_start + ref_grid_off + q];
+                for (int m2 = 0; m2 < nm; ++m2) {
+                    q += S.in_ref[m2];
+                    if (++idx[m2] < S.in_n[m2]) break;
+                    q -= (int64_t)S.in_ref[m2] * S.in_n[m2];
+                    idx[m2] = 0;
+                }
             }
         }
         std::sort(ent.begin(), ent.end());
@@ -672,29 +742,31 @@ static int build_fast_path(evr_sg4_plan *p, int nb_Term, const int32_t *term_mod
             pdst[j] = ent[j].second;
         }
     }
-    if (!ok) return 0;
-    // launch configuration per size class + "next term" prefetch links
+    // launch configuration per (size class, flavour) + "next item" prefetch links
     if (evr::fast_set_attributes()) return 1;
     if (iso && evr::iso_set_attributes()) return 1;
     p->n_classes = 0;
     {
+        const int class_gsize[4] = {envi("EVR_SG4_G0", 256), envi("EVR_SG4_G1", 128), envi("EVR_SG4_G2", 64), envi("EVR_SG4_G3", 32)};
         int w0 = 0;
-        for (int ci = 0; ci < 13; ++ci) {
-            const int c = (ci == 0) ? 12 : ci - 1;              // same order as the sort above
+        while (w0 < n_items) {
+            const int szc = batches[w0].szclass, fl = batches[w0].flavour;
             int w1 = w0;
-            int64_t cap = 1;
-            while (w1 < p->n_terms && class_of(forder[w1]) == c) { cap = std::max<int64_t>(cap, (int64_t)fterms[w1].nq * nb0); ++w1; }
-            if (w1 == w0) continue;
+            int64_t cap = 1, nqmax = 1;
+            while (w1 < n_items && batches[w1].szclass == szc && batches[w1].flavour == fl) {
+                cap = std::max<int64_t>(cap, (int64_t)fterms[w1].nq * nb0);
+                nqmax = std::max<int64_t>(nqmax, fterms[w1].nq);
+                ++w1;
+            }
+            if (p->n_classes >= EVR_MAX_FCLASSES) return 0;
             {   // the psi buffer also stages the scatter map (6 bytes per entry of the slice padded to 32 entries)
-                int64_t nqmax = 1;
-                for (int w = w0; w < w1; ++w) nqmax = std::max<int64_t>(nqmax, fterms[w].nq);
                 const int64_t nq32 = (nqmax + 31) & ~(int64_t)31;
                 cap = std::max<int64_t>(cap, (nq32 * 3 + 3) / 4);
             }
             cap = (cap + 3) & ~(int64_t)3;                      // the gather stores whole quads
-            const bool rt = (c >= 3 && c < 6), tri = (c >= 6 && c < 9), iso_class = iso && (c >= 9 || (tri && iso_big));
-            const int gsize = class_gsize[c];
+            const bool rt = (fl == 1), tri = (fl == 2), iso_class = iso && (fl == 3 || (tri && iso_big));
             const int max_threads = tri ? EVR_FAST_MAX_THREADS_TRI : EVR_FAST_MAX_THREADS;
+            const int gsize = std::min(class_gsize[szc], max_threads);
             const size_t per_group = (size_t)2 * cap * sizeof(double) + 2 * sizeof(evr::FastTermDev);
             const size_t pool_bytes = (pool_in_smem && !iso_class) ? pool.size() * sizeof(double) : 0;
             const size_t budget = 227 * 1024;
@@ -723,6 +795,7 @@ static int build_fast_path(evr_sg4_plan *p, int nb_Term, const int32_t *term_mod
             w0 = w1;
         }
     }
+    p->n_fitems = n_items;
     cudaFree(p->d_fterms); cudaFree(p->d_fmap); cudaFree(p->d_fmats); cudaFree(p->d_fV);
     p->d_fterms = nullptr; p->d_fmap = nullptr; p->d_fmats = nullptr; p->d_fV = nullptr;
     if (upload(&p->d_fterms, fterms.data(), fterms.size())) return 1;
@@ -735,7 +808,7 @@ static int build_fast_path(evr_sg4_plan *p, int nb_Term, const int32_t *term_mod
     if (upload(&p->d_fmats, pool.data(), pool.size())) return 1;
     if (Vgrid && upload(&p->d_fV, fV.data(), fV.size())) return 1;
     evr::FastPlanDev &f = p->fpd;
-    f.nb0 = nb0; f.n_terms = p->n_terms; f.has_V = Vgrid ? 1 : 0; f.pool_len = (int)pool.size();
+    f.nb0 = nb0; f.n_terms = p->n_fitems; f.has_V = Vgrid ? 1 : 0; f.pool_len = (int)pool.size();
     p->fast_pool_in_smem = pool_in_smem;
     p->fast_iso = iso && std::any_of(term_iso.begin(), term_iso.end(), [](char c) { return c != 0; });
     p->iso_blocks.swap(iso_blocks);
@@ -935,7 +1008,7 @@ static int launch(evr_sg4_plan *p, int npsi, const double *d_psi_user, double *d
     CUDA_TRY(cudaMemsetAsync(d_Hpsi, 0, bytes, st));                 // reference zeroes OpPsi (:765)
     if (p->n_terms > 0) {
         if (p->fast) {
-            if ((long long)p->n_terms * npsi > INT_MAX) return fail("evr_sg4_apply: n_terms * npsi exceeds 2^31 work items");
+            if ((long long)p->n_fitems * npsi > INT_MAX) return fail("evr_sg4_apply: n_terms * npsi exceeds 2^31 work items");
             if (p->fast_iso && evr::iso_bind(p->device, p->iso_id, p->iso_blocks.data(), st)) return 1;
             const bool multi = p->n_classes > 1 && p->ev_fork != nullptr;
             if (multi) CUDA_TRY(cudaEventRecord(p->ev_fork, st));
@@ -1077,7 +1150,7 @@ extern "C" int evr_sg4_plan_destroy(evr_sg4_plan **pp)
     cudaFree(p->d_fpos); cudaFree(p->d_gmap); cudaFree(p->d_perm); cudaFree(p->d_psi_int); cudaFree(p->d_Hpsi_int);
     cudaFree(p->d_GG); cudaFree(p->d_Jac); cudaFree(p->d_sq);
     if (p->stream) cudaStreamDestroy(p->stream);
-    for (int c = 0; c < 13; ++c) { if (p->side[c]) cudaStreamDestroy(p->side[c]); if (p->ev_join[c]) cudaEventDestroy(p->ev_join[c]); }
+    for (int c = 0; c < EVR_MAX_FCLASSES; ++c) { if (p->side[c]) cudaStreamDestroy(p->side[c]); if (p->ev_join[c]) cudaEventDestroy(p->ev_join[c]); }
     if (p->ev_fork) cudaEventDestroy(p->ev_fork);
     delete p;
     *pp = nullptr;

@@ -403,3 +403,58 @@ def test_peer_memory_allreduce_kernel_single_device(evr, np_, n):
     for b in bufs:
         assert torch.equal(b, want)
     assert evr.lib.lib().evr_sg4_allreduce_slices(ptrs, 0, 0, n, st) != 0      # bad arguments fail loudly
+
+
+# ---- the benchmarked configuration itself (BASELINE.json configs[4] at LB=LG=6 and 7, default plan settings):
+# block-ordered packed vector, batched work items of every size class, iso + pool-based instantiations side by side
+_BENCH_CACHE = {}
+
+
+def _bench_case(evr, L):
+    if L not in _BENCH_CACHE:
+        basis, op = evr.workloads.henon_heiles(12, L)
+        psi = random_psi(basis.nb, 1)
+        import os as _os
+        ref = oracle_apply(op, psi, nthreads=max(1, len(_os.sched_getaffinity(0))))
+        _BENCH_CACHE[L] = (basis, op, psi, ref)
+    return _BENCH_CACHE[L]
+
+
+@pytest.mark.parametrize("L", [6, 7])
+def test_benchmarked_configuration_parity(evr, L):
+    basis, op, psi, ref = _bench_case(evr, L)
+    assert basis.nqq == {6: 4195284, 7: 23826372}[L]
+    out = op.apply_host(psi)
+    assert op.info(evr.lib.INFO_PATH) == 1 and op.info(evr.lib.INFO_ISO) == 1
+    assert rel_l2(out[0], ref[0]) < TOL, rel_l2(out[0], ref[0])
+
+
+@pytest.mark.parametrize("L,nranks", [(6, 8), (7, 8)])
+def test_benchmarked_configuration_term_ranges_of_8_ranks(evr, L, nranks):
+    """The N = 8 decomposition of bench.py (points-balanced contiguous term ranges): the partial sums of the eight
+    plans add up to the oracle's full H|psi>."""
+    basis, op, psi, ref = _bench_case(evr, L)
+    acc = np.zeros_like(ref)
+    prev = 0
+    for r in range(nranks):
+        lo, hi = evr.distributed.balanced_iGs(basis.tab_nq_OF_SRep, nranks, r)
+        assert lo == prev
+        prev = hi
+        part = evr.ParamOp(basis, 1, op.OpGrid, iG_range=(lo, hi))
+        acc += part.apply_host(psi)
+        part.close()
+    assert prev == basis.nb_SG
+    assert rel_l2(acc[0], ref[0]) < TOL, rel_l2(acc[0], ref[0])
+
+
+def test_batched_and_unbatched_work_items_agree(evr, monkeypatch):
+    """Batches of same-schedule terms (default) vs one term per work item (EVR_SG4_BATCH=0), several right-hand sides."""
+    basis, op = evr.workloads.henon_heiles(9, 4)
+    psi = random_psi(basis.nb, 3, 11)
+    a = op.apply_host(psi)
+    monkeypatch.setenv("EVR_SG4_BATCH", "0")
+    op2 = evr.ParamOp(basis, 1, op.OpGrid)
+    b = op2.apply_host(psi)
+    ref = oracle_apply(op, psi)
+    for i in range(3):
+        assert rel_l2(a[i], ref[i]) < TOL and rel_l2(b[i], ref[i]) < TOL

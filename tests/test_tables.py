@@ -103,3 +103,20 @@ def test_balanced_iGs_partitions_by_cost(evr):
             prev = hi
         assert prev == b.nb_SG and sum(loads) == b.nqq
         assert max(loads) - min(loads) <= 2 * int(cost.max())
+
+
+@pytest.mark.parametrize("L", [6, 7])
+def test_product_tables_bit_exact_with_oracle_benchmarked_sizes(L, evr):
+    """The benchmarked configuration (HH 12-D, LB = LG = 6 and 7: 18 564 / 50 388 terms, 4.2 M / 23.8 M entries of
+    tab_iB_OF_SRep_TO_iB): the product's closed-form tables against the oracle's enumeration + search, bit-exact."""
+    b = evr.workloads.hm_sg4_basis(12, L, L, 1, 2)
+    t = Tables(12, L, L, 1, 2)
+    expect = {6: (18564, 369305, 4195284), 7: (50388, 1392065, 23826372)}[L]
+    assert (b.nb_SG, b.nb, b.nqq) == expect == (t.nb_SG, t.nb, t.NQ)
+    assert (b.Max_Srep, b.count0, b.Lmin) == (t.S, t.count0, t.Lmin)
+    assert np.array_equal(b.nDind_SmolyakRep_Tab_nDval, t.tab_l)
+    assert np.array_equal(b.WeightSG, t.weight)
+    assert np.array_equal(b.tab_nq_OF_SRep, t.tab_nq) and np.array_equal(b.tab_nb_OF_SRep, t.tab_nb)
+    assert np.array_equal(b.tab_Sum_nq_OF_SRep, t.sum_nq) and np.array_equal(b.tab_Sum_nb_OF_SRep, t.sum_nb)
+    assert np.array_equal(b.nDindB_Tab_nDval, t.packedB)
+    assert np.array_equal(b.tab_iB_OF_SRep_TO_iB, t.map)
