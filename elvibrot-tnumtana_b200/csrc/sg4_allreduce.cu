@@ -6,6 +6,7 @@
 // every element crosses NVLink once in and once out).  All ranks end up with bit-identical vectors.  The caller
 // brackets the launch with two cross-rank barriers on the stream (all partial sums complete / all slices written).
 #include <algorithm>
+#include <string>
 #include <cuda_runtime.h>
 #include "sg4_internal.h"
 #include "../../include/evr_sg4_comm.h"
@@ -40,7 +41,136 @@ sg4_allreduce_slice_kernel(const PeerPtrs P, const int np_rt, const long long lo
     }
 }
 
+// slice `rank` of the local buffer <- sum over the np buffers (reduce-scatter half; fixed order 0..np-1)
+template <int NP>
+__global__ void __launch_bounds__(256)
+sg4_reduce_slice_kernel(const PeerPtrs P, const int np_rt, const int rank, double *__restrict__ dst,
+                        const long long lo2, const long long hi2, const long long tail)
+{
+    const int np = (NP > 0) ? NP : np_rt;
+    for (long long i = lo2 + blockIdx.x * (long long)blockDim.x + threadIdx.x; i < hi2; i += (long long)gridDim.x * blockDim.x) {
+        double2 v[(NP > 0) ? NP : EVR_SG4_MAX_PEERS];
+#pragma unroll
+        for (int r = 0; r < ((NP > 0) ? NP : EVR_SG4_MAX_PEERS); ++r)
+            if (r < np) v[r] = __ldcg(reinterpret_cast<const double2 *>(P.p[r]) + i);
+        double2 s = v[0];
+#pragma unroll
+        for (int r = 1; r < ((NP > 0) ? NP : EVR_SG4_MAX_PEERS); ++r)
+            if (r < np) { s.x += v[r].x; s.y += v[r].y; }
+        reinterpret_cast<double2 *>(dst)[i] = s;
+    }
+    if (tail >= 0 && blockIdx.x == 0 && threadIdx.x == 0) {
+        double s = __ldcg(P.p[0] + tail);
+        for (int r = 1; r < np; ++r) s += __ldcg(P.p[r] + tail);
+        dst[tail] = s;
+    }
+}
+
+// every slice but the local one <- the owner's copy (all-gather half; psi before the term kernels)
+__global__ void __launch_bounds__(256)
+sg4_allgather_kernel(const PeerPtrs P, const int np, const int rank, const long long n2, const long long chunk, const long long tail)
+{
+    double2 *dst = reinterpret_cast<double2 *>(P.p[rank]);
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n2; i += (long long)gridDim.x * blockDim.x) {
+        const int owner = (int)(i / chunk);
+        if (owner != rank) dst[i] = __ldcg(reinterpret_cast<const double2 *>(P.p[owner]) + i);
+    }
+    if (tail >= 0 && rank != np - 1 && blockIdx.x == 0 && threadIdx.x == 0) P.p[rank][tail] = __ldcg(P.p[np - 1] + tail);
+}
+
 } // namespace evr
+
+namespace {
+struct Slices { long long n2, chunk, lo2, hi2, tail; };
+Slices slices_of(int64_t n, int np, int rank)
+{
+    Slices S;
+    S.n2 = n / 2;                                               // double2 units
+    S.chunk = std::max<long long>(1, (S.n2 + np - 1) / np);
+    S.lo2 = std::min<long long>(S.n2, S.chunk * rank);
+    S.hi2 = std::min<long long>(S.n2, S.lo2 + S.chunk);
+    S.tail = ((n & 1) && rank == np - 1) ? n - 1 : -1;          // a last odd element belongs to the last rank
+    return S;
+}
+int peers_of(evr::PeerPtrs &P, const void *const *peer_ptrs, int np, const char *who)
+{
+    for (int r = 0; r < EVR_SG4_MAX_PEERS; ++r) {
+        P.p[r] = (r < np) ? static_cast<double *>(const_cast<void *>(peer_ptrs[r])) : nullptr;
+        if (r < np && (!P.p[r] || (reinterpret_cast<uintptr_t>(P.p[r]) & 15)))
+            return evr::fail(std::string(who) + ": peer buffers must be non-null and 16-byte aligned");
+    }
+    return 0;
+}
+int grid_for(long long work)
+{
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    return (int)std::min<long long>(std::max<long long>(1, (work + 255) / 256), (long long)sms * 8);
+}
+} // namespace
+
+extern "C" int evr_sg4_slice_bounds(int64_t n, int np, int rank, int64_t *lo, int64_t *hi)
+{
+    if (np < 1 || rank < 0 || rank >= np || n < 0 || !lo || !hi) return evr::fail("evr_sg4_slice_bounds: bad arguments");
+    const Slices S = slices_of(n, np, rank);
+    *lo = 2 * S.lo2;
+    *hi = (rank == np - 1) ? n : 2 * S.hi2;
+    return 0;
+}
+
+extern "C" int evr_sg4_allgather_slices(const void *const *peer_ptrs, int np, int rank, int64_t n, void *cuda_stream)
+{
+    using namespace evr;
+    if (np < 1 || np > EVR_SG4_MAX_PEERS || rank < 0 || rank >= np || n < 0 || !peer_ptrs)
+        return fail("evr_sg4_allgather_slices: bad arguments");
+    PeerPtrs P;
+    if (peers_of(P, peer_ptrs, np, "evr_sg4_allgather_slices")) return 1;
+    if (n == 0 || np == 1) return 0;
+    const Slices S = slices_of(n, np, rank);
+    const long long tail = (n & 1) ? n - 1 : -1;
+    sg4_allgather_kernel<<<grid_for(S.n2), 256, 0, static_cast<cudaStream_t>(cuda_stream)>>>(P, np, rank, S.n2, S.chunk, tail);
+    if (cudaGetLastError() != cudaSuccess) return fail("evr_sg4_allgather_slices: kernel launch failed");
+    return 0;
+}
+
+static int reduce_launch(const evr::PeerPtrs &P, int np, int rank, double *dst, long long lo2, long long hi2, long long tail, cudaStream_t st)
+{
+    using namespace evr;
+    if (hi2 <= lo2 && tail < 0) return 0;
+    const int grid = grid_for(hi2 - lo2);
+    switch (np) {
+    case 2: sg4_reduce_slice_kernel<2><<<grid, 256, 0, st>>>(P, np, rank, dst, lo2, hi2, tail); break;
+    case 4: sg4_reduce_slice_kernel<4><<<grid, 256, 0, st>>>(P, np, rank, dst, lo2, hi2, tail); break;
+    case 8: sg4_reduce_slice_kernel<8><<<grid, 256, 0, st>>>(P, np, rank, dst, lo2, hi2, tail); break;
+    default: sg4_reduce_slice_kernel<0><<<grid, 256, 0, st>>>(P, np, rank, dst, lo2, hi2, tail); break;
+    }
+    if (cudaGetLastError() != cudaSuccess) return fail("evr_sg4_reduce: kernel launch failed");
+    return 0;
+}
+
+extern "C" int evr_sg4_reduce_slice(const void *const *peer_ptrs, int np, int rank, int64_t n, void *cuda_stream)
+{
+    using namespace evr;
+    if (np < 1 || np > EVR_SG4_MAX_PEERS || rank < 0 || rank >= np || n < 0 || !peer_ptrs)
+        return fail("evr_sg4_reduce_slice: bad arguments");
+    PeerPtrs P;
+    if (peers_of(P, peer_ptrs, np, "evr_sg4_reduce_slice")) return 1;
+    if (n == 0 || np == 1) return 0;
+    const Slices S = slices_of(n, np, rank);
+    return reduce_launch(P, np, rank, P.p[rank], S.lo2, S.hi2, S.tail, static_cast<cudaStream_t>(cuda_stream));
+}
+
+extern "C" int evr_sg4_reduce_to(const void *const *peer_ptrs, int np, int64_t n, double *dst, void *cuda_stream)
+{
+    using namespace evr;
+    if (np < 1 || np > EVR_SG4_MAX_PEERS || n < 0 || !peer_ptrs || !dst || (reinterpret_cast<uintptr_t>(dst) & 15))
+        return fail("evr_sg4_reduce_to: bad arguments");
+    PeerPtrs P;
+    if (peers_of(P, peer_ptrs, np, "evr_sg4_reduce_to")) return 1;
+    if (n == 0) return 0;
+    return reduce_launch(P, np, 0, dst, 0, n / 2, (n & 1) ? n - 1 : -1, static_cast<cudaStream_t>(cuda_stream));
+}
 
 extern "C" int evr_sg4_allreduce_slices(const void *const *peer_ptrs, int np, int rank, int64_t n, void *cuda_stream)
 {

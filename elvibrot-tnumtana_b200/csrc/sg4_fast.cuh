@@ -554,7 +554,7 @@ __device__ __forceinline__ void dispatch_pass(const int tmpl, const int n1, cons
 // latency of one group's gather/scatter is hidden by the arithmetic of the other groups on the SM;
 // the next term's mapping and V slices are pulled into L2 one term ahead (prefetch.global.L2).
 //
-// dynamic smem:  pool[pool_len] (MS only) | per group: psi[cap] | acc[cap] | FastTermDev[2]
+// dynamic smem:  pool[pool_len] (MS only) | per group: psi[cap] | acc[cap] | FastTermDev[2] | mbarrier[2]
 __device__ __forceinline__ void group_sync(const int gsize, const int group)
 {
     if (gsize == 32) __syncwarp();
@@ -577,7 +577,32 @@ __device__ __forceinline__ void cp_async8_zfill(void *dst, const void *src, cons
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_commit_wait_all() { asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory"); }
 
-#define EVR_GB 6            // gather/scatter batch: independent loads in flight per lane
+// ---- bulk asynchronous copies (TMA 1-D, cp.async.bulk -> SASS UBLKCP) completing on an mbarrier: one thread moves a
+// whole contiguous, 16-byte aligned slice (gather map, V, scatter map + positions) without any LSU instruction
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, const int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, const unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, const unsigned bytes, unsigned long long *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, const unsigned parity)
+{
+    unsigned done;
+    do {
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    } while (!done);
+}
+// generic-proxy accesses (LDS/STS) to a buffer are ordered before the async-proxy writes of a following bulk copy
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 template <int MS, bool RT, bool TRI>
 __global__ void __launch_bounds__(TRI ? EVR_FAST_MAX_THREADS_TRI : EVR_FAST_MAX_THREADS, 1)
@@ -591,12 +616,19 @@ sg4_term_kernel_fast(const FastPlanDev P, const FastClassDev Cc, const int npsi,
     const int tid = threadIdx.x - group * gsize;
     const int cap = Cc.cap;
     const int pool_doubles = (MS == 1) ? P.pool_len : 0;
-    const size_t per_group = (size_t)2 * cap * sizeof(double) + 2 * sizeof(FastTermDev);
+    const size_t per_group = (size_t)2 * cap * sizeof(double) + 2 * sizeof(FastTermDev) + EVR_FAST_MBAR_BYTES;
     double *s_pool = reinterpret_cast<double *>(smem_raw);
     unsigned char *gbase = smem_raw + (size_t)pool_doubles * sizeof(double) + per_group * group;
     double *s_psi = reinterpret_cast<double *>(gbase);
     double *s_acc = s_psi + cap;
     FastTermDev *s_T0 = reinterpret_cast<FastTermDev *>(s_acc + cap);
+    unsigned long long *s_bar = reinterpret_cast<unsigned long long *>(s_T0 + 2);   // [0]: map slices, [1]: V slice
+    if (tid == 0) {
+        mbar_init(s_bar, 1);
+        mbar_init(s_bar + 1, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    unsigned ph_map = 0, ph_v = 0;      // phase parities of the two mbarriers
 
     if (MS == 1) {   // the whole (de-duplicated) 1-D matrix pool lives in shared memory for the kernel's lifetime
         for (int i = threadIdx.x; i < P.pool_len; i += blockDim.x) s_pool[i] = __ldg(P.mats + i);
@@ -664,34 +696,40 @@ sg4_term_kernel_fast(const FastPlanDev P, const FastClassDev Cc, const int npsi,
                 //  (2) every lane reads its quads of map entries from shared memory and issues the packed-psi copies
                 //      (8-byte LDGSTS, zero-fill for dropped functions / padding) straight into the psi buffer, then - once
                 //      all lanes have read the map - the V slice streams into the acc buffer (16-byte chunks); one wait.
-                const int nq4 = (nq + 3) >> 2;
-                {
-                    const char *src = reinterpret_cast<const char *>(gm);
-                    char *dst = reinterpret_cast<char *>(s_acc);
-                    for (int c = tid; c < nq4; c += gsize) cp_async16(dst + 16 * c, src + 16 * c);
-                    cp_async_commit_wait_all();
-                    group_sync(gsize, group);
+                const unsigned nq32u = (unsigned)((nq + 31) & ~31);
+                if (tid == 0) {                     // (the group barrier at the top of the item ordered all earlier accesses)
+                    fence_proxy_async();
+                    mbar_expect_tx(s_bar, nq32u * 4u);
+                    bulk_g2s(s_acc, gm, nq32u * 4u, s_bar);
                 }
+                mbar_wait(s_bar, ph_map); ph_map ^= 1;
                 {
-                    const int4 *gq = reinterpret_cast<const int4 *>(s_acc);
+                    // consecutive lanes take consecutive entries: every LDGSTS writes 32 consecutive doubles (2 shared-memory
+                    // wavefronts; the quad-per-lane layout cost 11.7, ncu round 2) and neighbouring entries share L2 sectors
+                    const int *gi = reinterpret_cast<const int *>(s_acc);
                     const bool nox = (P.dbg & 16) != 0;
-                    for (int c = tid; c < nq4; c += gsize) {
-                        const int4 m = gq[c];
-                        double *d = s_psi + 4 * c;
-                        cp_async8_zfill(d, x + max(m.x, 0), (m.x >= 0 && !nox) ? 8 : 0);
-                        cp_async8_zfill(d + 1, x + max(m.y, 0), (m.y >= 0 && !nox) ? 8 : 0);
-                        cp_async8_zfill(d + 2, x + max(m.z, 0), (m.z >= 0 && !nox) ? 8 : 0);
-                        cp_async8_zfill(d + 3, x + max(m.w, 0), (m.w >= 0 && !nox) ? 8 : 0);
+                    int e = tid;
+                    for (; e + 3 * gsize < nq; e += 4 * gsize) {
+                        int m[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) m[u] = gi[e + u * gsize];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) cp_async8_zfill(s_psi + e + u * gsize, x + max(m[u], 0), (m[u] >= 0 && !nox) ? 8 : 0);
+                    }
+                    for (; e < nq; e += gsize) {
+                        const int m = gi[e];
+                        cp_async8_zfill(s_psi + e, x + max(m, 0), (m >= 0 && !nox) ? 8 : 0);
                     }
                     group_sync(gsize, group);
                 }
-                if (hasV && !(P.dbg & 32)) {
-                    const char *src = reinterpret_cast<const char *>(Vt);
-                    char *dst = reinterpret_cast<char *>(s_acc);
-                    const int nq2 = (nq + 1) >> 1;
-                    for (int c = tid; c < nq2; c += gsize) cp_async16(dst + 16 * c, src + 16 * c);
+                const bool stageV = hasV && !(P.dbg & 32);
+                if (stageV && tid == 0) {           // all lanes have read the map: the V slice may overwrite it
+                    fence_proxy_async();
+                    mbar_expect_tx(s_bar + 1, nq32u * 8u);
+                    bulk_g2s(s_acc, Vt, nq32u * 8u, s_bar + 1);
                 }
                 cp_async_commit_wait_all();
+                if (stageV) { mbar_wait(s_bar + 1, ph_v); ph_v ^= 1; }
             } else {
                 for (int j = tid; j < nq; j += gsize) {
                     const int m = __ldg(gm + j);
@@ -712,18 +750,19 @@ sg4_term_kernel_fast(const FastPlanDev P, const FastClassDev Cc, const int npsi,
             // (2 B/entry) of the term stream into that buffer while the remaining G -> B passes run
             const int nq32 = (nq + 31) & ~31;
             const bool local_scatter = (P.dbg & 128) != 0 && nb0 == 1;
-            auto stage_scatter_map = [&]() {
-                char *dst = reinterpret_cast<char *>(s_psi);
-                const char *sm = reinterpret_cast<const char *>(mp), *sp = reinterpret_cast<const char *>(pp);
-                const int c_map = nq32 >> 2, c_all = c_map + (nq32 >> 3);
-                if (local_scatter) {     // scatter in term-local order: the gather map is the scatter map, no positions
-                    const char *sg = reinterpret_cast<const char *>(gm);
-                    for (int c = tid; c < c_map; c += gsize) cp_async16(dst + 16 * c, sg + 16 * c);
-                } else {
-                    for (int c = tid; c < c_all; c += gsize)
-                        cp_async16(dst + 16 * c, (c < c_map) ? sm + 16 * c : sp + 16 * (c - c_map));
+            auto stage_scatter_map = [&]() {          // called behind a group barrier: nobody reads the psi buffer any more
+                if (tid == 0) {
+                    char *dst = reinterpret_cast<char *>(s_psi);
+                    fence_proxy_async();
+                    if (local_scatter) {     // scatter in term-local order: the gather map is the scatter map, no positions
+                        mbar_expect_tx(s_bar, (unsigned)nq32 * 4u);
+                        bulk_g2s(dst, gm, (unsigned)nq32 * 4u, s_bar);
+                    } else {
+                        mbar_expect_tx(s_bar, (unsigned)nq32 * 6u);
+                        bulk_g2s(dst, mp, (unsigned)nq32 * 4u, s_bar);
+                        bulk_g2s(dst + (size_t)nq32 * 4, pp, (unsigned)nq32 * 2u, s_bar);
+                    }
                 }
-                cp_async_commit();
             };
             if (G == 0) {
                 if (tid < nb0) s_acc[tid] = (T->vshift + (hasV ? s_acc[tid] : 0.0)) * s_psi[tid];
@@ -800,8 +839,7 @@ sg4_term_kernel_fast(const FastPlanDev P, const FastClassDev Cc, const int npsi,
             // neighbouring addresses, the FP64 reductions of a warp share L2 sectors); map and positions come from the
             // staged copy in the psi buffer; padding / dropped entries carry index -1
             {
-                cp_async_commit_wait_all();
-                group_sync(gsize, group);
+                mbar_wait(s_bar, ph_map); ph_map ^= 1;      // (the barrier behind the last pass made acc visible)
                 const double weight = T->weight;
                 const int *s_map = reinterpret_cast<const int *>(s_psi);
                 const unsigned short *s_pos = reinterpret_cast<const unsigned short *>(s_psi) + 2 * nq32;

@@ -9,6 +9,7 @@ namespace evr {
 
 #define EVR_MAXG 8          // max groups (<= 16 active modes) per term on the fast path
 #define EVR_MAX_FCLASSES 16 // (size class, kernel flavour) pairs = launches per H|psi> on the fast path
+#define EVR_FAST_MBAR_BYTES 16 // two mbarriers per thread group (bulk copies of the map / V slices)
 #define EVR_RT_NMAX 16      // runtime-size single-mode tiles keep up to 16 values in registers
 
 struct FastGroup {
@@ -83,5 +84,14 @@ int iso_bind(int device, int id, const double *blocks, cudaStream_t st);
 // big_tiles: the 512-thread instantiation with the 3x3x3 / 5x5 / 3x7 / 3x9 tiles, else the 768-thread one (tiles <= 15 values)
 int iso_launch(bool big_tiles, int nctas, int nthr, size_t smem, cudaStream_t st,
                const FastPlanDev &P, const FastClassDev &C, int npsi, const double *psi, double *Hpsi);
+
+// second-generation kernel (sg4_fast2.cuh): nb0 = 1, iso flavour (sg4_v2_iso.cu) or shared-memory pool (sg4_v2_pool.cu)
+int v2_iso_set_attributes();
+int v2_iso_bind(int device, int id, const double *blocks, cudaStream_t st);
+int v2_iso_launch(int nctas, int nthr, size_t smem, cudaStream_t st,
+                  const FastPlanDev &P, const FastClassDev &C, int npsi, const double *psi, double *Hpsi);
+int v2_pool_set_attributes();
+int v2_pool_launch(int nctas, int nthr, size_t smem, cudaStream_t st,
+                   const FastPlanDev &P, const FastClassDev &C, int npsi, const double *psi, double *Hpsi);
 
 } // namespace evr

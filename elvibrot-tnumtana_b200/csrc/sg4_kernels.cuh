@@ -99,7 +99,7 @@ __device__ __forceinline__ void mode_product(const double *__restrict__ M, int n
 // dynamic smem: [2 or 3 * cap doubles][ints: nq_of,nb_of,offB,offG (4*D*(LG+1))][per-term ints 5*D + 3*(D+1)]
 //               [3 ints per operator term]
 #define EVR_GEN_SMEM_INTS(nT, D, nop) (4 * (nT) + 5 * (D) + 3 * ((D) + 1) + 3 * (nop))
-__global__ void __launch_bounds__(256, 4)
+static __global__ void __launch_bounds__(256, 4)
 sg4_term_kernel_generic(const PlanDev P, const GenClassDev Cc, const int npsi,
                         const double *__restrict__ psi, double *__restrict__ Hpsi)
 {
@@ -357,7 +357,7 @@ struct Op10Dev {
 #define EVR_OP10_PTS 8           // grid points per thread kept in registers (nq <= 8*256)
 
 // dynamic smem: bufA[cap] | bufB[cap] | R[n_act][nqmax] | chi[nqmax] | ints (as the generic kernel)
-__global__ void __launch_bounds__(256)
+static __global__ void __launch_bounds__(256)
 sg4_term_kernel_type10(const PlanDev P, const Op10Dev O, const int npsi,
                        const double *__restrict__ psi, double *__restrict__ Hpsi)
 {

@@ -4,10 +4,7 @@
 // Replaces the body of sub_TabOpPsi_FOR_SGtype4 (sub_Operator/sub_OpPsi_SG4.f90:678-979) and of
 // Action_MPI_S1 minus its reduce (sub_OpPsi_SG4_MPI.f90:454-571).  No CPU fallback exists: every
 // entry point fails with a message if CUDA is unavailable.
-#include "../../include/evr_sg4.h"
-#include "sg4_internal.h"
-#include "sg4_kernels.cuh"
-#include "sg4_fast_types.h"
+#include "sg4_plan.h"
 
 #include <cuda_runtime.h>
 
@@ -36,79 +33,6 @@ using evr::fail;
 
 extern "C" int evr_sg4_version(void) { return 100; }
 extern "C" const char *evr_sg4_last_error(void) { return evr::g_err.c_str(); }
-
-struct evr_sg4_plan {
-    int device = 0;
-    int D = 0, nb_SG = 0, nb0 = 1, LG = 0;
-    int64_t nb = 0;
-    int iG_begin = 0, iG_end = 0, n_terms = 0;
-    int64_t S_local = 0, NQ_local = 0, NQ_total = 0;
-    int64_t grid_start = 0;                 // first grid point of the range in the full Smolyak grid
-    int cap = 0;                            // doubles per smem buffer (incl. nb0)
-    int sm_count = 0;
-    bool op_set = false;
-    int type_Op = 1, n_opterms = 0, n_var = 0;
-    int64_t launches = 0;
-    int64_t flops_npsi1 = 0;
-    // host copies needed later
-    std::vector<int32_t> h_tab_l, h_nq_of, h_nb_of, h_tab_nq, h_tab_nb;
-    std::vector<int> order;                 // work order -> local term index
-    std::vector<int32_t> h_map;             // mapping slice of the range (reference order)
-    std::vector<int64_t> h_map_off, h_grid_off;   // per local term (reference order)
-    std::vector<double> h_B, h_BTw, h_D1, h_D2, h_weight;
-    std::vector<int32_t> h_offB, h_offG;
-    // fast path (sg4_fast.cuh)
-    bool fast = false;
-    evr::FastTermDev *d_fterms = nullptr;
-    int32_t *d_fmap = nullptr;           // per term: internal packed index (sorted ascending), -1 = dropped
-    int32_t *d_gmap = nullptr;           // per term: internal packed index in term-local (internal layout) order
-    uint16_t *d_fpos = nullptr;          // per term: term-local position of each sorted entry
-    int32_t *d_perm = nullptr;           // internal packed order -> reference packed index (0-based)
-    double *d_psi_int = nullptr, *d_Hpsi_int = nullptr;   // packed vectors in the internal (block) order
-    int64_t int_cap = 0;
-    double *d_fmats = nullptr, *d_fV = nullptr;
-    evr::FastPlanDev fpd{};
-    std::vector<double> h_cost;             // per local term
-    std::vector<int64_t> h_tsize;           // per local term: prod max(nq_k, nb_k)
-    int n_classes = 0;
-    bool fast_pool_in_smem = false;
-    bool fast_block_order = false;
-    bool fast_iso = false;                  // constant-matrix instantiation (sg4_iso.cu)
-    std::vector<double> iso_blocks;         // its [B|BTw|T] blocks, bound to the __constant__ array before each launch
-    int iso_id = 0;
-    int n_fitems = 0;                       // work items (batches of same-schedule terms) of the fast path
-    evr::FastClassDev fclass[EVR_MAX_FCLASSES];
-    size_t fclass_smem[EVR_MAX_FCLASSES] = {0};
-    int fclass_ctas[EVR_MAX_FCLASSES] = {0};
-    bool fclass_is_iso[EVR_MAX_FCLASSES] = {false};
-    int fclass_flavour[EVR_MAX_FCLASSES] = {0};        // 0 templated, 1 runtime-size, 2 cube tiles (plain) / iso with large tiles, 3 iso
-    // device
-    evr::TermDev *d_terms = nullptr;
-    uint8_t *d_lev = nullptr;
-    int32_t *d_map = nullptr, *d_nq_of = nullptr, *d_nb_of = nullptr, *d_offB = nullptr, *d_offG = nullptr;
-    double *d_B = nullptr, *d_BTw = nullptr, *d_D1 = nullptr, *d_D2 = nullptr;
-    evr::OpTermDev *d_opterms = nullptr;
-    double *d_grids = nullptr;
-    double *d_psi = nullptr, *d_Hpsi = nullptr;   // staging for the host-buffer entry point
-    // type_Op = 10
-    bool op10 = false;
-    evr::Op10Dev o10{};
-    double *d_GG = nullptr, *d_Jac = nullptr, *d_sq = nullptr;
-    size_t smem10 = 0;
-    int ctas10_max = 0;
-    int64_t stage_cap = 0;
-    cudaStream_t stream = nullptr;
-    cudaStream_t side[EVR_MAX_FCLASSES] = {nullptr};   // class kernels overlap their tails
-    cudaEvent_t ev_fork = nullptr, ev_join[EVR_MAX_FCLASSES] = {nullptr};
-    size_t smem_bytes = 0;
-    int grid_ctas = 0, gen_ctas_max = 0;
-    // generic kernel: one launch per term-size class (CTA of 256/128/64/32 threads)
-    int n_gclasses = 0;
-    evr::GenClassDev gclass[4];
-    int gclass_threads[4] = {0}, gclass_occ[4] = {0};
-    size_t gclass_smem[4] = {0};
-    evr::PlanDev pd{};
-};
 
 template <class T>
 static int upload(T **dptr, const T *h, size_t n)
@@ -172,6 +96,23 @@ extern "C" int evr_sg4_plan_create(evr_sg4_plan **out, int device,
                                    const int32_t *nq_of, const int32_t *nb_of,
                                    const double *B, const double *BTw, const double *D1, const double *D2,
                                    int iG_begin, int iG_end)
+{
+    // evr_sg4_set_devices(n > 1): a plan on the default device (device < 0) spans the first n devices
+    if (device < 0 && evr::multi_devices() > 1)
+        return evr::multi_create(out, D, nb_SG, nb0, nb, LG, tab_l, WeightSG, tab_nq, tab_nb, tab_iB, nq_of, nb_of, B, BTw, D1, D2,
+                                 iG_begin, iG_end);
+    return evr::plan_create_single(out, device, D, nb_SG, nb0, nb, LG, tab_l, WeightSG, tab_nq, tab_nb, tab_iB, nq_of, nb_of,
+                                   B, BTw, D1, D2, iG_begin, iG_end);
+}
+
+int evr::plan_create_single(evr_sg4_plan **out, int device,
+                            int D, int nb_SG, int nb0, int64_t nb, int LG,
+                            const int32_t *tab_l, const double *WeightSG,
+                            const int32_t *tab_nq, const int32_t *tab_nb,
+                            const int32_t *tab_iB,
+                            const int32_t *nq_of, const int32_t *nb_of,
+                            const double *B, const double *BTw, const double *D1, const double *D2,
+                            int iG_begin, int iG_end)
 {
     if (!out || !tab_l || !WeightSG || !tab_nq || !tab_nb || !tab_iB || !nq_of || !nb_of || !B || !BTw || !D1 || !D2)
         return fail("evr_sg4_plan_create: null argument");
@@ -502,6 +443,7 @@ static int build_fast_path(evr_sg4_plan *p, int nb_Term, const int32_t *term_mod
         for (int64_t i = 0; i < p->nb; ++i) inv_perm[perm[i]] = (int32_t)i;
     }
     // ---- per-term schedule: active modes -> register-tile groups, internal (permuted) term layout ---------------
+    const int max35 = (nb0 == 1 && envi("EVR_SG4_V2", 0) != 0) ? envi("EVR_SG4_MAX35", 1) : 1000;
     struct TermSched {
         evr::FastTermDev F;                     // nq = points of ONE term; offsets filled per batch below
         std::vector<int> in_n, in_ref;          // per internal mode: size, stride in the reference term layout
@@ -545,7 +487,10 @@ static int build_fast_path(evr_sg4_plan *p, int nb_Term, const int32_t *term_mod
                 else grp.push_back({a, -1, -1});
             }
             while (iso_big && i5.size() >= 2) { grp.push_back({i5[i5.size() - 2], i5[i5.size() - 1], -1}); i5.pop_back(); i5.pop_back(); }
-            while (!iso_big && !i5.empty() && !i3.empty()) { grp.push_back({i3.back(), i5.back(), -1}); i3.pop_back(); i5.pop_back(); }
+            // second-generation kernel: the 15-value tile only as the first (stride-1) group -- the later forward passes keep
+            // two tiles in registers (psi and the carried kinetic accumulator) and must stay within 80 registers
+            int n35 = 0;
+            while (!iso_big && !i5.empty() && !i3.empty() && (n35 < max35)) { grp.push_back({i3.back(), i5.back(), -1}); i3.pop_back(); i5.pop_back(); ++n35; }
             while (!iso_big && !i5.empty()) { grp.push_back({i5.back(), -1, -1}); i5.pop_back(); }
             if (!i5.empty()) {
                 if (!i3.empty()) { grp.push_back({i3.back(), i5[0], -1}); i3.pop_back(); }
@@ -633,8 +578,11 @@ static int build_fast_path(evr_sg4_plan *p, int nb_Term, const int32_t *term_mod
     // descriptor, and the batch's map / V slices are contiguous.  Every term of a shape qualifies when the modes of equal
     // size share their 1-D basis (iso flavour: the kernel ignores the matrix offsets); otherwise only terms on modes with
     // identical matrices do.  The batch capacity adapts to the problem size so that small grids still fill the GPU.
+    // second-generation kernel (sg4_fast2.cuh): single channel, iso tiles or pool-in-shared-memory tiles
+    const bool v2_on = nb0 == 1 && envi("EVR_SG4_V2", 0) != 0;   // experimental, off by default
+    auto flavour_v2 = [&](int fl) { return v2_on && ((fl == 3 && iso && !iso_big) || (fl == 0 && pool_in_smem)); };
     auto term_is_iso = [&](int t) { const int fl = flavour_of(t); return iso && (fl == 3 || (fl == 2 && iso_big)); };
-    const int64_t bcap_max = std::max(1, envi("EVR_SG4_BCAP", 4700));                   // doubles per psi/acc buffer
+    const int64_t bcap_max = std::max(1, envi("EVR_SG4_BCAP", v2_on ? 3700 : 2350));                   // doubles per psi/acc buffer
     const int64_t target_items = (int64_t)p->sm_count * std::max(1, envi("EVR_SG4_ITEMS_PER_SM", 16));
     const int64_t bcap = std::max<int64_t>(1, std::min<int64_t>(bcap_max, (p->NQ_local * nb0 + target_items - 1) / target_items));
     struct Batch { std::vector<int> terms; int flavour, szclass; int64_t size; double cost; };
@@ -736,6 +684,7 @@ static int build_fast_path(evr_sg4_plan *p, int nb_Term, const int32_t *term_mod
                 }
             }
         }
+        if (flavour_v2(Bt.flavour)) continue;             // scatters through the gather map: no sorted map / positions
         std::sort(ent.begin(), ent.end());
         for (int j = 0; j < F.nq; ++j) {
             mdst[j] = (ent[j].first == INT32_MAX) ? -1 : ent[j].first;
@@ -745,6 +694,7 @@ static int build_fast_path(evr_sg4_plan *p, int nb_Term, const int32_t *term_mod
     // launch configuration per (size class, flavour) + "next item" prefetch links
     if (evr::fast_set_attributes()) return 1;
     if (iso && evr::iso_set_attributes()) return 1;
+    if (v2_on && (evr::v2_iso_set_attributes() || evr::v2_pool_set_attributes())) return 1;
     p->n_classes = 0;
     {
         const int class_gsize[4] = {envi("EVR_SG4_G0", 256), envi("EVR_SG4_G1", 128), envi("EVR_SG4_G2", 64), envi("EVR_SG4_G3", 32)};
@@ -760,16 +710,19 @@ static int build_fast_path(evr_sg4_plan *p, int nb_Term, const int32_t *term_mod
             }
             if (p->n_classes >= EVR_MAX_FCLASSES) return 0;
             {   // the psi buffer also stages the scatter map (6 bytes per entry of the slice padded to 32 entries)
+                // and the bulk copies move whole padded slices (map: 4 B, V: 8 B per entry) into the acc buffer
                 const int64_t nq32 = (nqmax + 31) & ~(int64_t)31;
-                cap = std::max<int64_t>(cap, (nq32 * 3 + 3) / 4);
+                cap = std::max<int64_t>(cap, std::max<int64_t>((nq32 * 3 + 3) / 4, nq32));
             }
             cap = (cap + 3) & ~(int64_t)3;                      // the gather stores whole quads
             const bool rt = (fl == 1), tri = (fl == 2), iso_class = iso && (fl == 3 || (tri && iso_big));
-            const int max_threads = tri ? EVR_FAST_MAX_THREADS_TRI : EVR_FAST_MAX_THREADS;
+            const int max_threads = tri ? EVR_FAST_MAX_THREADS_TRI : (flavour_v2(fl) ? envi("EVR_SG4_V2_THREADS", 768) : EVR_FAST_MAX_THREADS);
             const int gsize = std::min(class_gsize[szc], max_threads);
-            const size_t per_group = (size_t)2 * cap * sizeof(double) + 2 * sizeof(evr::FastTermDev);
+            const size_t per_group = flavour_v2(fl) ? ((size_t)cap * 20 + 2 * sizeof(evr::FastTermDev) + EVR_FAST_MBAR_BYTES)
+                                                    : ((size_t)2 * cap * sizeof(double) + 2 * sizeof(evr::FastTermDev) + EVR_FAST_MBAR_BYTES);
             const size_t pool_bytes = (pool_in_smem && !iso_class) ? pool.size() * sizeof(double) : 0;
-            const size_t budget = 227 * 1024;
+            // (experiment: a smaller budget leaves part of the unified 256 KB array to the L1 cache, where register spills live)
+            const size_t budget = (size_t)std::min(227, std::max(16, envi("EVR_SG4_SMEM_KB", 227))) * 1024;
             if (pool_bytes + per_group > budget) return 0;
             int ngrp = (int)std::min<size_t>((budget - pool_bytes) / per_group, (size_t)(max_threads / gsize));
             if (gsize > 32) ngrp = std::min(ngrp, 15);          // named barriers 1..15
@@ -791,6 +744,7 @@ static int build_fast_path(evr_sg4_plan *p, int nb_Term, const int32_t *term_mod
             p->fclass_smem[p->n_classes] = smem; p->fclass_ctas[p->n_classes] = ctas;
             p->fclass_flavour[p->n_classes] = iso_class ? (tri ? 2 : 3) : (rt ? 1 : (tri ? 2 : 0));
             p->fclass_is_iso[p->n_classes] = iso_class;
+            p->fclass_v2[p->n_classes] = flavour_v2(fl);
             ++p->n_classes;
             w0 = w1;
         }
@@ -828,6 +782,7 @@ extern "C" int evr_sg4_plan_set_op(evr_sg4_plan *p, int type_Op, int nb_Term, co
                                    const double *Mat_cte, const double *const *grids)
 {
     if (!p) return fail("evr_sg4_plan_set_op: null plan");
+    if (!p->sub.empty()) return evr::multi_set_op(p, type_Op, nb_Term, term_mode, grid_zero, grid_cte, Mat_cte, grids);
     if (type_Op != 0 && type_Op != 1)
         return fail("evr_sg4_plan_set_op: type_Op must be 0 or 1 (use evr_sg4_plan_set_op10 for type_Op=10)");
     if (nb_Term < 1 || !grid_zero || !grid_cte) return fail("evr_sg4_plan_set_op: bad term list");
@@ -923,6 +878,7 @@ extern "C" int evr_sg4_plan_set_op10(evr_sg4_plan *p, int n_act, const int32_t *
                                      const double *V, const double *GG, const double *Jac, const double *sq)
 {
     if (!p) return fail("evr_sg4_plan_set_op10: null plan");
+    if (!p->sub.empty()) return evr::multi_set_op10(p, n_act, act_mode, V, GG, Jac, sq);
     if (n_act < 1 || n_act > EVR_MAXD || !act_mode || !GG || !Jac || !sq) return fail("evr_sg4_plan_set_op10: bad arguments");
     CUDA_TRY(cudaSetDevice(p->device));
     const int nb0 = p->nb0;
@@ -953,7 +909,12 @@ extern "C" int evr_sg4_plan_set_op10(evr_sg4_plan *p, int n_act, const int32_t *
     O.has_V = V ? 1 : 0;
     if (V) { if (up_slice(&p->d_grids, V, nb0 * nb0)) return 1; }
     O.V = p->d_grids; O.GG = p->d_GG; O.Jac = p->d_Jac; O.sq = p->d_sq;
-    CUDA_TRY(cudaFuncSetAttribute(evr::sg4_term_kernel_type10, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem10));
+    {   // the attribute belongs to the function, not to the plan: never lower it under another live plan
+        static size_t attr10_max[64] = {0};
+        size_t &amax = attr10_max[p->device & 63];
+        amax = std::max(amax, p->smem10);
+        CUDA_TRY(cudaFuncSetAttribute(evr::sg4_term_kernel_type10, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)amax));
+    }
     int occ = 0;
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, evr::sg4_term_kernel_type10, 256, p->smem10));
     if (occ < 1) return fail("evr_sg4_plan_set_op10: kernel cannot be resident");
@@ -1009,7 +970,10 @@ static int launch(evr_sg4_plan *p, int npsi, const double *d_psi_user, double *d
     if (p->n_terms > 0) {
         if (p->fast) {
             if ((long long)p->n_fitems * npsi > INT_MAX) return fail("evr_sg4_apply: n_terms * npsi exceeds 2^31 work items");
-            if (p->fast_iso && evr::iso_bind(p->device, p->iso_id, p->iso_blocks.data(), st)) return 1;
+            bool any_v1_iso = false, any_v2_iso = false;
+            for (int c = 0; c < p->n_classes; ++c) if (p->fclass_is_iso[c]) (p->fclass_v2[c] ? any_v2_iso : any_v1_iso) = true;
+            if (any_v1_iso && evr::iso_bind(p->device, p->iso_id, p->iso_blocks.data(), st)) return 1;
+            if (any_v2_iso && evr::v2_iso_bind(p->device, p->iso_id, p->iso_blocks.data(), st)) return 1;
             const bool multi = p->n_classes > 1 && p->ev_fork != nullptr;
             if (multi) CUDA_TRY(cudaEventRecord(p->ev_fork, st));
             for (int c = 0; c < p->n_classes; ++c) {
@@ -1019,7 +983,11 @@ static int launch(evr_sg4_plan *p, int npsi, const double *d_psi_user, double *d
                 const bool ms = p->fast_pool_in_smem, rt = p->fclass[c].rt != 0, tri = p->fclass[c].tri != 0;
                 const int nctas = p->fclass_ctas[c], nthr = p->fclass[c].cta_threads;
                 const size_t sm = p->fclass_smem[c];
-                if (p->fclass_is_iso[c]) { if (evr::iso_launch(tri, nctas, nthr, sm, st, p->fpd, p->fclass[c], npsi, d_psi, d_Hpsi)) return 1; }
+                if (p->fclass_v2[c]) {
+                    if (p->fclass_is_iso[c]) { if (evr::v2_iso_launch(nctas, nthr, sm, st, p->fpd, p->fclass[c], npsi, d_psi, d_Hpsi)) return 1; }
+                    else if (evr::v2_pool_launch(nctas, nthr, sm, st, p->fpd, p->fclass[c], npsi, d_psi, d_Hpsi)) return 1;
+                }
+                else if (p->fclass_is_iso[c]) { if (evr::iso_launch(tri, nctas, nthr, sm, st, p->fpd, p->fclass[c], npsi, d_psi, d_Hpsi)) return 1; }
                 else if (evr::fast_launch(ms ? 1 : 0, rt, tri, nctas, nthr, sm, st, p->fpd, p->fclass[c], npsi, d_psi, d_Hpsi)) return 1;
                 p->launches += 1;
                 if (multi && c > 0) {
@@ -1070,12 +1038,48 @@ static int launch(evr_sg4_plan *p, int npsi, const double *d_psi_user, double *d
     return 0;
 }
 
+int evr::plan_launch(evr_sg4_plan *p, int npsi, const double *d_psi, double *d_Hpsi, cudaStream_t st)
+{
+    return launch(p, npsi, d_psi, d_Hpsi, st);
+}
+int evr::scale_launch(long long n, double E0, double Esc, const double *x, double *y, cudaStream_t st)
+{
+    const int thr = 256;
+    const int blocks = (int)std::max<long long>(1, std::min<long long>((n + thr - 1) / thr, 148 * 16));
+    evr::sg4_scale_kernel<<<blocks, thr, 0, st>>>(n, E0, Esc, x, y);
+    return cudaGetLastError() == cudaSuccess ? 0 : fail("evr_sg4: scale kernel launch failed");
+}
+int evr::plan_ensure_staging(evr_sg4_plan *p, int64_t n)
+{
+    if (n <= p->stage_cap) return 0;
+    if (p->d_psi) cudaFree(p->d_psi);
+    if (p->d_Hpsi) cudaFree(p->d_Hpsi);
+    p->d_psi = p->d_Hpsi = nullptr; p->stage_cap = 0;
+    CUDA_TRY(cudaMalloc((void **)&p->d_psi, (size_t)n * sizeof(double)));
+    CUDA_TRY(cudaMalloc((void **)&p->d_Hpsi, (size_t)n * sizeof(double)));
+    p->stage_cap = n;
+    return 0;
+}
+
+// [psi, psi+n) and [Hpsi, Hpsi+n) must not overlap: the result vector is zeroed before psi is gathered
+static bool ranges_overlap(const double *a, const double *b, int64_t n)
+{
+    const uintptr_t x = reinterpret_cast<uintptr_t>(a), y = reinterpret_cast<uintptr_t>(b), len = (uintptr_t)n * sizeof(double);
+    return x < y + len && y < x + len;
+}
+
 extern "C" int evr_sg4_apply_device(evr_sg4_plan *p, int npsi, const double *d_psi, double *d_Hpsi, void *cuda_stream)
 {
     if (!p) return fail("evr_sg4_apply_device: null plan");
+    if (!p->sub.empty()) {
+        if (!d_psi || !d_Hpsi || npsi < 1) return fail("evr_sg4_apply_device: bad arguments");
+        return evr::multi_apply_device(p, npsi, d_psi, d_Hpsi, (cudaStream_t)cuda_stream, false, 0.0, 1.0);
+    }
     if (!p->op_set) return fail("evr_sg4_apply_device: operator not set (call evr_sg4_plan_set_op)");
     if (npsi < 1) return fail("evr_sg4_apply: size(Psi) = 0");     // reference: STOP (:738-743)
     if (!d_psi || !d_Hpsi) return fail("evr_sg4_apply_device: null buffer");
+    if (ranges_overlap(d_psi, d_Hpsi, (int64_t)npsi * p->nb * p->nb0))
+        return fail("evr_sg4_apply_device: psi and Hpsi overlap (the action is not in-place)");
     CUDA_TRY(cudaSetDevice(p->device));
     return launch(p, npsi, d_psi, d_Hpsi, (cudaStream_t)cuda_stream);
 }
@@ -1084,10 +1088,15 @@ extern "C" int evr_sg4_apply_device_scaled(evr_sg4_plan *p, int npsi, const doub
                                            double E0, double Esc, void *cuda_stream)
 {
     if (!p) return fail("evr_sg4_apply_device_scaled: null plan");
+    if (!p->sub.empty()) {
+        if (!d_psi || !d_Hpsi || npsi < 1 || Esc == 0.0) return fail("evr_sg4_apply_device_scaled: bad arguments");
+        return evr::multi_apply_device(p, npsi, d_psi, d_Hpsi, (cudaStream_t)cuda_stream, true, E0, Esc);
+    }
     if (!p->op_set) return fail("evr_sg4_apply_device_scaled: operator not set (call evr_sg4_plan_set_op)");
     if (npsi < 1) return fail("evr_sg4_apply: size(Psi) = 0");
     if (!d_psi || !d_Hpsi) return fail("evr_sg4_apply_device_scaled: null buffer");
-    if (d_psi == d_Hpsi) return fail("evr_sg4_apply_device_scaled: psi and Hpsi must be different buffers");
+    if (ranges_overlap(d_psi, d_Hpsi, (int64_t)npsi * p->nb * p->nb0))
+        return fail("evr_sg4_apply_device_scaled: psi and Hpsi overlap (the action is not in-place)");
     if (Esc == 0.0) return fail("evr_sg4_apply_device_scaled: Esc = 0");
     CUDA_TRY(cudaSetDevice(p->device));
     return launch(p, npsi, d_psi, d_Hpsi, (cudaStream_t)cuda_stream, ScaleArgs{true, E0, Esc});
@@ -1096,19 +1105,18 @@ extern "C" int evr_sg4_apply_device_scaled(evr_sg4_plan *p, int npsi, const doub
 extern "C" int evr_sg4_apply(evr_sg4_plan *p, int npsi, const double *psi, double *Hpsi)
 {
     if (!p) return fail("evr_sg4_apply: null plan");
+    if (!p->sub.empty()) {
+        if (!psi || !Hpsi) return fail("evr_sg4_apply: null buffer");
+        if (npsi < 1) return fail("evr_sg4_apply: size(Psi) = 0");
+        return evr::multi_apply_host(p, npsi, psi, Hpsi);
+    }
     if (!p->op_set) return fail("evr_sg4_apply: operator not set (call evr_sg4_plan_set_op)");
     if (npsi < 1) return fail("evr_sg4_apply: size(Psi) = 0");
     if (!psi || !Hpsi) return fail("evr_sg4_apply: null buffer");
     CUDA_TRY(cudaSetDevice(p->device));
     const int64_t n = (int64_t)npsi * p->nb * p->nb0;
-    if (n > p->stage_cap) {
-        if (p->d_psi) cudaFree(p->d_psi);
-        if (p->d_Hpsi) cudaFree(p->d_Hpsi);
-        p->d_psi = p->d_Hpsi = nullptr; p->stage_cap = 0;
-        CUDA_TRY(cudaMalloc((void **)&p->d_psi, (size_t)n * sizeof(double)));
-        CUDA_TRY(cudaMalloc((void **)&p->d_Hpsi, (size_t)n * sizeof(double)));
-        p->stage_cap = n;
-    }
+    if (ranges_overlap(psi, Hpsi, n)) return fail("evr_sg4_apply: psi and Hpsi overlap (the action is not in-place)");
+    if (evr::plan_ensure_staging(p, n)) return 1;
     CUDA_TRY(cudaMemcpyAsync(p->d_psi, psi, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, p->stream));
     if (launch(p, npsi, p->d_psi, p->d_Hpsi, p->stream)) return 1;
     CUDA_TRY(cudaMemcpyAsync(Hpsi, p->d_Hpsi, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
@@ -1119,6 +1127,7 @@ extern "C" int evr_sg4_apply(evr_sg4_plan *p, int npsi, const double *psi, doubl
 extern "C" int64_t evr_sg4_plan_info(const evr_sg4_plan *p, int what)
 {
     if (!p) return -1;
+    if (!p->sub.empty()) return evr::multi_info(p, what);
     const int64_t nb0 = p->nb0;
     switch (what) {
     case EVR_INFO_LAUNCHES: return p->launches;
@@ -1142,6 +1151,7 @@ extern "C" int evr_sg4_plan_destroy(evr_sg4_plan **pp)
 {
     if (!pp || !*pp) return 0;
     evr_sg4_plan *p = *pp;
+    if (!p->sub.empty()) { evr::multi_destroy(p); delete p; *pp = nullptr; return 0; }
     cudaSetDevice(p->device);
     cudaFree(p->d_terms); cudaFree(p->d_lev); cudaFree(p->d_map); cudaFree(p->d_nq_of); cudaFree(p->d_nb_of);
     cudaFree(p->d_offB); cudaFree(p->d_offG); cudaFree(p->d_B); cudaFree(p->d_BTw); cudaFree(p->d_D1); cudaFree(p->d_D2);

@@ -67,7 +67,8 @@ class TermParallelOp:
                 grp = self.group if self.group is not None else dist.group.WORLD
                 t = symm_mem.empty(*shape, dtype=torch.float64, device=dev)
                 hdl = symm_mem.rendezvous(t, grp)
-                ok = 1 if (hdl.world_size == self.world and hdl.rank == self.rank and t.data_ptr() % 16 == 0) else 0
+                ok = 1 if (hdl.world_size == self.world and hdl.rank == self.rank and t.data_ptr() % 16 == 0
+                            and int(hdl.buffer_ptrs[self.rank]) == t.data_ptr()) else 0
             except Exception as e:      # noqa: BLE001 - any failure means "use NCCL", agreed on by all ranks below
                 self._symm_error = repr(e)
                 ok = 0
@@ -99,6 +100,29 @@ class TermParallelOp:
                    "evr_sg4_allreduce_slices")
         hdl.barrier(channel=1)      # every slice has been written everywhere
         return out
+
+    def apply_host_slices(self, psi_host, out_host, d_psi, d_out):
+        """Host-resident caller at N > 1: this rank copies only ITS slice of the (replicated) host psi to the device, the
+        slices are all-gathered over NVLink, every rank applies its terms, and after the reduce-scatter this rank returns
+        only its slice of H psi to ``out_host`` (the other entries of ``out_host`` are left untouched) -- the N PCIe links
+        carry 1/N of the vector each.  ``d_psi`` / ``d_out`` must come from ``symmetric_empty``.  Returns the [lo, hi) slice."""
+        import torch
+        ep, eo = self._symm.get(d_psi.data_ptr()), self._symm.get(d_out.data_ptr())
+        if ep is None or eo is None:
+            raise RuntimeError("apply_host_slices needs peer-mapped device buffers (TermParallelOp.symmetric_empty)")
+        n = d_psi.numel()
+        lo, hi = _lib.slice_bounds(n, self.world, self.rank)
+        st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        L = _lib.lib()
+        d_psi.view(-1)[lo:hi].copy_(psi_host.view(-1)[lo:hi], non_blocking=True)
+        ep[1].barrier(channel=0)                                    # every rank's slice is on its device
+        _lib.check(L.evr_sg4_allgather_slices(ep[2], self.world, self.rank, n, st), "evr_sg4_allgather_slices")
+        self._local(d_psi, d_out)
+        eo[1].barrier(channel=0)                                    # every rank's partial sum is complete
+        _lib.check(L.evr_sg4_reduce_slice(eo[2], self.world, self.rank, n, st), "evr_sg4_reduce_slice")
+        out_host.view(-1)[lo:hi].copy_(d_out.view(-1)[lo:hi], non_blocking=True)
+        eo[1].barrier(channel=1)                                    # peers are done reading this rank's buffers
+        return lo, hi
 
     def _cuda_apply(self, psi, out):
         import torch

@@ -18,7 +18,7 @@ _lib = None
 TAB_NB_SG, TAB_NB, TAB_S, TAB_NQ, TAB_COUNT0, TAB_LMIN = 0, 1, 2, 3, 4, 5
 TAB_TAB_L, TAB_WEIGHT, TAB_TAB_NQ, TAB_TAB_NB, TAB_SUM_NQ, TAB_SUM_NB, TAB_PACKEDB, TAB_MAP = 10, 11, 12, 13, 14, 15, 16, 17
 INFO_LAUNCHES, INFO_ALG_BYTES_NPSI1, INFO_ALG_BYTES_PER_RHS_EXTRA, INFO_NQ_LOCAL, INFO_S_LOCAL = 0, 1, 2, 3, 4
-INFO_SMEM_BYTES, INFO_GRID_CTAS, INFO_PATH, INFO_FLOPS_NPSI1, INFO_ISO = 5, 6, 7, 8, 9
+INFO_SMEM_BYTES, INFO_GRID_CTAS, INFO_PATH, INFO_FLOPS_NPSI1, INFO_ISO, INFO_DEVICES = 5, 6, 7, 8, 9, 10
 
 EXPORTS = [
     "evr_sg4_version", "evr_sg4_last_error",
@@ -26,7 +26,8 @@ EXPORTS = [
     "evr_sg4_ini_iGs", "evr_sg4_balanced_iGs",
     "evr_sg4_plan_create", "evr_sg4_plan_set_op", "evr_sg4_plan_set_op10", "evr_sg4_apply", "evr_sg4_apply_device", "evr_sg4_apply_device_scaled",
     "evr_sg4_plan_info", "evr_sg4_plan_destroy",
-    "evr_sg4_allreduce_slices",
+    "evr_sg4_allreduce_slices", "evr_sg4_allgather_slices", "evr_sg4_reduce_slice", "evr_sg4_reduce_to", "evr_sg4_slice_bounds",
+    "evr_sg4_set_devices", "evr_sg4_get_devices", "evr_sg4_host_register", "evr_sg4_host_unregister",
 ]
 
 
@@ -40,7 +41,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     srcs = [os.path.join(srcdir, f) for f in os.listdir(srcdir)] + [os.path.join(_HERE, "..", "include", "evr_sg4.h")]
     stale = (not os.path.exists(SO_PATH)) or any(os.path.getmtime(s) > os.path.getmtime(SO_PATH) for s in srcs)
     if force or stale:
-        cmd = ["make", "-j", "5", "-C", srcdir] + (["-B"] if force else [])
+        cmd = ["make", "-j", "8", "-C", srcdir] + (["-B"] if force else [])
         out = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
         if verbose or out.returncode != 0:
             print(out.stdout)
@@ -89,8 +90,35 @@ def lib():
     L.evr_sg4_plan_destroy.argtypes = [C.POINTER(vp)]
     L.evr_sg4_allreduce_slices.restype = i32
     L.evr_sg4_allreduce_slices.argtypes = [vp, i32, i32, i64, vp]
+    L.evr_sg4_allgather_slices.restype = i32
+    L.evr_sg4_allgather_slices.argtypes = [vp, i32, i32, i64, vp]
+    L.evr_sg4_reduce_slice.restype = i32
+    L.evr_sg4_reduce_slice.argtypes = [vp, i32, i32, i64, vp]
+    L.evr_sg4_reduce_to.restype = i32
+    L.evr_sg4_reduce_to.argtypes = [vp, i32, i64, vp, vp]
+    L.evr_sg4_slice_bounds.restype = i32
+    L.evr_sg4_slice_bounds.argtypes = [i64, i32, i32, C.POINTER(i64), C.POINTER(i64)]
+    L.evr_sg4_set_devices.restype = i32
+    L.evr_sg4_set_devices.argtypes = [i32]
+    L.evr_sg4_get_devices.restype = i32
+    L.evr_sg4_host_register.restype = i32
+    L.evr_sg4_host_register.argtypes = [vp, i64]
+    L.evr_sg4_host_unregister.restype = i32
+    L.evr_sg4_host_unregister.argtypes = [vp]
     _lib = L
     return L
+
+
+def set_devices(ndev: int):
+    """Plans created afterwards on the default device span the first ``ndev`` GPUs of the node (one process, NVLink peer
+    memory; C-ABI evr_sg4_set_devices)."""
+    check(lib().evr_sg4_set_devices(int(ndev)), "evr_sg4_set_devices")
+
+
+def slice_bounds(n: int, np_: int, rank: int):
+    lo, hi = C.c_int64(), C.c_int64()
+    check(lib().evr_sg4_slice_bounds(int(n), int(np_), int(rank), C.byref(lo), C.byref(hi)), "evr_sg4_slice_bounds")
+    return lo.value, hi.value
 
 
 def check(rc: int, what: str = ""):

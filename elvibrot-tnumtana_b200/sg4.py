@@ -251,9 +251,11 @@ class ParamOp:
             raise ValueError(f"psi has {psi.shape[1]} coefficients, basis has {n}")
         if out is None:
             out = np.empty_like(psi)
+        elif not (isinstance(out, np.ndarray) and out.dtype == np.float64 and out.flags.c_contiguous and out.size == psi.size):
+            raise ValueError("out must be a C-contiguous float64 array with as many elements as psi")
         _lib.check(_lib.lib().evr_sg4_apply(self.plan(), psi.shape[0], psi.ctypes.data, out.ctypes.data), "evr_sg4_apply")
         self.nb_OpPsi += psi.shape[0]
-        return out[0] if one else out
+        return (out[0] if out.ndim == 2 else out) if one else out
 
     def apply_device_ptr(self, npsi: int, d_psi: int, d_Hpsi: int, stream: int = 0):
         """Device-resident entry: raw device pointers (e.g. torch ``tensor.data_ptr()``) + CUDA stream."""

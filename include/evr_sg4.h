@@ -79,6 +79,22 @@ int evr_sg4_ini_iGs(int nb_SG, int np, int rank, int *iG_begin, int *iG_end);
 int evr_sg4_balanced_iGs(int nb_SG, const int32_t *cost, int np, int rank, int *iG_begin, int *iG_end);
 
 /* ---------------------------------------------------------------------------
+ * Several GPUs from ONE process (no MPI): after evr_sg4_set_devices(n), every plan created with device < 0 spans
+ * devices 0..n-1 of the node.  The plan's term range is split in n contiguous sub-ranges of equal grid points (the
+ * decomposition of the reference's MPI scheme 1, Action_MPI_S1, sub_Operator/sub_OpPsi_SG4_MPI.f90:454-571, with
+ * ini_iGs_MPI / auto_iGs_MPI ranges) and the partial results are summed over NVLink peer memory instead of
+ * MPI_Reduce_sum_Bcast (:535-560).  evr_sg4_apply then copies psi slice-wise (device d: slice d, all-gathered over NVLink)
+ * and returns H psi slice-wise, so the n PCIe links work in parallel; evr_sg4_apply_device[_scaled] expects psi / Hpsi on
+ * device 0.  Needs peer access between all pairs of the n devices; fails otherwise.  n = 1 restores single-device plans.
+ * evr_sg4_host_register page-locks a caller-owned host buffer (e.g. the shim's packed psi / Hpsi arrays) so that those
+ * copies are asynchronous; unregister before freeing it.
+ * ------------------------------------------------------------------------- */
+int evr_sg4_set_devices(int ndev);
+int evr_sg4_get_devices(void);
+int evr_sg4_host_register(void *ptr, int64_t bytes);
+int evr_sg4_host_unregister(void *ptr);
+
+/* ---------------------------------------------------------------------------
  * Plan = device-resident copy of everything sub_TabOpPsi_FOR_SGtype4 reads from
  * para_Op%BasisnD (param_SGType2, WeightSG, tab_basisPrimSG), for the terms
  * [iG_begin, iG_end) of this process (all terms: 0, nb_SG).
@@ -153,7 +169,8 @@ enum {                           /* 'what' for evr_sg4_plan_info */
     EVR_INFO_GRID_CTAS       = 6,   /* CTAs per launch                                 */
     EVR_INFO_PATH            = 7,   /* 0 = generic term kernel, 1 = constant-KEO fast path */
     EVR_INFO_FLOPS_NPSI1     = 8,   /* algorithmic flops of one H|psi>      */
-    EVR_INFO_ISO             = 9    /* 1 = fast path runs its constant-matrix instantiation (all modes of a size share one 1-D basis) */
+    EVR_INFO_ISO             = 9,   /* 1 = fast path runs its constant-matrix instantiation (all modes of a size share one 1-D basis) */
+    EVR_INFO_DEVICES         = 10   /* number of devices the plan spans (evr_sg4_set_devices) */
 };
 int64_t evr_sg4_plan_info(const evr_sg4_plan *plan, int what);
 int     evr_sg4_plan_destroy(evr_sg4_plan **plan);

@@ -21,6 +21,20 @@ extern "C" {
  * Returns 0, or non-zero with a message in evr_sg4_last_error(). */
 int evr_sg4_allreduce_slices(const void *const *peer_ptrs, int np, int rank, int64_t n, void *cuda_stream);
 
+/* The two halves separately, for callers whose input and output live in HOST memory (evr_sg4_apply with
+ * evr_sg4_set_devices, bench.py e2e at N > 1): every rank copies only its slice of psi host -> device, the slices are
+ * all-gathered over NVLink, and after the term kernels every rank reduces and returns only its slice of H psi, so that N
+ * PCIe links carry 1/N of the vector each.  Same slicing as evr_sg4_allreduce_slices: evr_sg4_slice_bounds gives the
+ * [lo, hi) range of doubles owned by `rank` (lo is even, i.e. 16-byte aligned; an odd last element goes to the last rank).
+ *   allgather_slices : every slice of peer_ptrs[rank] except its own <- the owner's buffer
+ *   reduce_slice     : slice `rank` of peer_ptrs[rank] <- sum over the np buffers (fixed order 0..np-1)
+ *   reduce_to        : dst[0..n) <- sum over the np buffers (device-resident caller on one device)
+ * All asynchronous on `cuda_stream`; the caller orders them against the other ranks' work (events / barriers). */
+int evr_sg4_slice_bounds(int64_t n, int np, int rank, int64_t *lo, int64_t *hi);
+int evr_sg4_allgather_slices(const void *const *peer_ptrs, int np, int rank, int64_t n, void *cuda_stream);
+int evr_sg4_reduce_slice(const void *const *peer_ptrs, int np, int rank, int64_t n, void *cuda_stream);
+int evr_sg4_reduce_to(const void *const *peer_ptrs, int np, int64_t n, double *dst, void *cuda_stream);
+
 #ifdef __cplusplus
 }
 #endif

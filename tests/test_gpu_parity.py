@@ -458,3 +458,108 @@ def test_batched_and_unbatched_work_items_agree(evr, monkeypatch):
     ref = oracle_apply(op, psi)
     for i in range(3):
         assert rel_l2(a[i], ref[i]) < TOL and rel_l2(b[i], ref[i]) < TOL
+
+
+def _ngpus():
+    import torch
+    return torch.cuda.device_count() if torch.cuda.is_available() else 0
+
+
+@pytest.mark.skipif(_ngpus() < 2, reason="needs two GPUs with peer access (gpurun --gpus 2)")
+@pytest.mark.parametrize("case", ["hh12d_L4", "hcn_generic", "pyrazine_nb0_2"])
+def test_set_devices_multi_gpu_plan_through_the_cabi(evr, case):
+    """evr_sg4_set_devices(2): one process, the plan spans two GPUs (term ranges of equal grid points), psi / H psi move
+    slice-wise, the partial sums are reduced over NVLink peer memory -- all through the C-ABI, no torch.distributed."""
+    import torch
+    ndev = min(_ngpus(), 4)
+    if case == "hh12d_L4":
+        basis, op1 = evr.workloads.henon_heiles(12, 4)
+        npsi = 3
+    elif case == "hcn_generic":
+        basis = evr.workloads.hm_sg4_basis(3, 4, 5, [10, 1, 1], [10, 2, 2])
+        op1 = evr.workloads.synthetic_curvilinear(basis)
+        npsi = 2
+    else:
+        basis, op1 = evr.workloads.pyrazine_12d(2)
+        npsi = 2
+    psi = random_psi(basis.nb * basis.nb0, npsi, 21)
+    ref = oracle_apply(op1, psi)
+    evr.lib.set_devices(ndev)
+    try:
+        opn = evr.ParamOp(basis, op1.type_Op, op1.OpGrid, mode_of_Qact=op1.mode_of_Qact)
+        out = opn.apply_host(psi)
+        assert opn.info(evr.lib.INFO_DEVICES) == ndev
+        assert opn.info(evr.lib.INFO_NQ_LOCAL) == basis.nqq
+        for i in range(npsi):
+            assert rel_l2(out[i], ref[i]) < TOL, (i, rel_l2(out[i], ref[i]))
+        # device-resident entry: psi / Hpsi on device 0
+        x = torch.from_numpy(psi).cuda(0)
+        y = torch.empty_like(x)
+        opn.apply_device_ptr(npsi, x.data_ptr(), y.data_ptr(), torch.cuda.current_stream(0).cuda_stream)
+        torch.cuda.synchronize(0)
+        for i in range(npsi):
+            assert rel_l2(y[i].cpu().numpy(), ref[i]) < TOL
+        # pinned (registered) host buffers: same result, repeated calls
+        L = evr.lib.lib()
+        xh, yh = np.ascontiguousarray(psi), np.empty_like(psi)
+        evr.lib.check(L.evr_sg4_host_register(xh.ctypes.data, xh.nbytes))
+        evr.lib.check(L.evr_sg4_host_register(yh.ctypes.data, yh.nbytes))
+        for _ in range(3):
+            opn.apply_host(xh, out=yh)
+        evr.lib.check(L.evr_sg4_host_unregister(xh.ctypes.data))
+        evr.lib.check(L.evr_sg4_host_unregister(yh.ctypes.data))
+        assert rel_l2(yh, ref) < TOL
+        opn.close()
+    finally:
+        evr.lib.set_devices(1)
+
+
+def test_peer_kernels_allgather_and_reduce_single_device(evr):
+    """evr_sg4_allgather_slices / evr_sg4_reduce_slice / evr_sg4_reduce_to on buffers of ONE device standing in for the peers
+    (the kernels only see pointers): slice bounds, odd lengths, bit-exact sums in the fixed order."""
+    import torch
+    L = evr.lib.lib()
+    for np_, n in [(2, 1001), (3, 4096), (8, 12345), (4, 7), (1, 5)]:
+        g = torch.Generator().manual_seed(n)
+        bufs = [torch.randn(n, dtype=torch.float64, generator=g).cuda() for _ in range(np_)]
+        orig = [b.clone() for b in bufs]
+        ptrs = (C.c_void_p * np_)(*[b.data_ptr() for b in bufs])
+        st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        bounds = [evr.lib.slice_bounds(n, np_, r) for r in range(np_)]
+        assert bounds[0][0] == 0 and bounds[-1][1] == n and all(bounds[r][1] == bounds[r + 1][0] for r in range(np_ - 1))
+        assert all(lo % 2 == 0 for lo, _ in bounds)
+        # reduce_to: plain sum in the order 0..np-1
+        dst = torch.empty(n, dtype=torch.float64, device="cuda")
+        evr.lib.check(L.evr_sg4_reduce_to(ptrs, np_, n, dst.data_ptr(), st))
+        ref = orig[0].clone()
+        for r in range(1, np_):
+            ref += orig[r]
+        assert torch.equal(dst, ref)
+        # reduce_slice by every "rank": slice r of buffer r holds the sum, everything else untouched
+        for r in range(np_):
+            evr.lib.check(L.evr_sg4_reduce_slice(ptrs, np_, r, n, st))
+        torch.cuda.synchronize()
+        for r, (lo, hi) in enumerate(bounds):
+            if np_ > 1:
+                assert torch.equal(bufs[r][lo:hi], ref[lo:hi])
+                mask = torch.ones(n, dtype=torch.bool, device="cuda")
+                mask[lo:hi] = False
+                assert torch.equal(bufs[r][mask], orig[r][mask])
+        # allgather: every buffer ends up with the owners' slices
+        want = torch.cat([bufs[r][lo:hi] for r, (lo, hi) in enumerate(bounds)]).clone()
+        for r in range(np_):
+            evr.lib.check(L.evr_sg4_allgather_slices(ptrs, np_, r, n, st))
+        torch.cuda.synchronize()
+        for r in range(np_):
+            assert torch.equal(bufs[r], want)
+
+
+def test_in_place_call_is_rejected(evr):
+    import torch
+    basis, op = evr.workloads.henon_heiles(4, 2)
+    x = torch.zeros(basis.nb, dtype=torch.float64, device="cuda")
+    with pytest.raises(evr.EvrSg4Error, match="overlap"):
+        op.apply_device_ptr(1, x.data_ptr(), x.data_ptr())
+    h = np.zeros(basis.nb)
+    with pytest.raises(evr.EvrSg4Error, match="overlap"):
+        op.apply_host(h, out=h)
