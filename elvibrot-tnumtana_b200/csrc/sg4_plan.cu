@@ -105,6 +105,36 @@ extern "C" int evr_sg4_plan_create(evr_sg4_plan **out, int device,
                                    B, BTw, D1, D2, iG_begin, iG_end);
 }
 
+// MPI scheme 1 of the reference keeps only the rank's slice of the mapping table
+// (Mapping_table_allocate_MPI, sub_Basis_SG4/sub_module_basis_BtoG_GtoB_SG4_MPI.f90:62-77: tab_iB_OF_SRep_TO_iB(bounds_MPI(1,id):bounds_MPI(2,id))):
+// tab_iB points at global entry tab_iB_first (0-based) and holds tab_iB_len entries, which must cover the plan's term range.
+extern "C" int evr_sg4_plan_create_ex(evr_sg4_plan **out, int device,
+                                      int D, int nb_SG, int nb0, int64_t nb, int LG,
+                                      const int32_t *tab_l, const double *WeightSG,
+                                      const int32_t *tab_nq, const int32_t *tab_nb,
+                                      const int32_t *tab_iB, int64_t tab_iB_first, int64_t tab_iB_len,
+                                      const int32_t *nq_of, const int32_t *nb_of,
+                                      const double *B, const double *BTw, const double *D1, const double *D2,
+                                      int iG_begin, int iG_end)
+{
+    if (!tab_iB || !tab_nb || tab_iB_first < 0 || tab_iB_len < 0) return fail("evr_sg4_plan_create_ex: bad mapping-table slice");
+    if (nb_SG < 1 || iG_begin < 0 || iG_end > nb_SG || iG_begin > iG_end) return fail("evr_sg4_plan_create_ex: bad term range");
+    int64_t first = 0, last = 0;
+    for (int iG = 0; iG < iG_end; ++iG) { if (iG < iG_begin) first += tab_nb[iG]; last += tab_nb[iG]; }
+    if (first < tab_iB_first || last > tab_iB_first + tab_iB_len)
+        return fail("evr_sg4_plan_create_ex: the mapping-table slice does not cover the term range [iG_begin, iG_end)");
+    // the single-device builder only reads entries [first, last) of the (virtual) full table
+    return evr_sg4_plan_create(out, device, D, nb_SG, nb0, nb, LG, tab_l, WeightSG, tab_nq, tab_nb, tab_iB - tab_iB_first,
+                               nq_of, nb_of, B, BTw, D1, D2, iG_begin, iG_end);
+}
+
+extern "C" int evr_sg4_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
 int evr::plan_create_single(evr_sg4_plan **out, int device,
                             int D, int nb_SG, int nb0, int64_t nb, int LG,
                             const int32_t *tab_l, const double *WeightSG,

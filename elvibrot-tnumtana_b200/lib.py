@@ -24,10 +24,13 @@ EXPORTS = [
     "evr_sg4_version", "evr_sg4_last_error",
     "evr_sg4_tables_build", "evr_sg4_tables_destroy", "evr_sg4_tables_size", "evr_sg4_tables_get",
     "evr_sg4_ini_iGs", "evr_sg4_balanced_iGs",
-    "evr_sg4_plan_create", "evr_sg4_plan_set_op", "evr_sg4_plan_set_op10", "evr_sg4_apply", "evr_sg4_apply_device", "evr_sg4_apply_device_scaled",
+    "evr_sg4_plan_create", "evr_sg4_plan_create_ex", "evr_sg4_device_count", "evr_sg4_plan_set_op", "evr_sg4_plan_set_op10", "evr_sg4_apply", "evr_sg4_apply_device", "evr_sg4_apply_device_scaled",
     "evr_sg4_plan_info", "evr_sg4_plan_destroy",
+    "evr_sg4_BtoG", "evr_sg4_GtoB", "evr_sg4_DerivOp_G", "evr_sg4_BtoG_device", "evr_sg4_GtoB_device", "evr_sg4_DerivOp_G_device",
     "evr_sg4_allreduce_slices", "evr_sg4_allgather_slices", "evr_sg4_reduce_slice", "evr_sg4_reduce_to", "evr_sg4_slice_bounds",
     "evr_sg4_set_devices", "evr_sg4_get_devices", "evr_sg4_host_register", "evr_sg4_host_unregister",
+    "evr_sg4_vec_alloc", "evr_sg4_vec_free", "evr_sg4_vec_upload", "evr_sg4_vec_download", "evr_sg4_vec_gram", "evr_sg4_vec_lincomb",
+    "evr_sg4_vec_scale", "evr_sg4_vec_precond", "evr_sg4_vec_schmidt",
 ]
 
 
@@ -74,6 +77,9 @@ def lib():
     L.evr_sg4_balanced_iGs.argtypes = [i32, vp, i32, i32, C.POINTER(i32), C.POINTER(i32)]
     L.evr_sg4_plan_create.restype = i32
     L.evr_sg4_plan_create.argtypes = [C.POINTER(vp), i32, i32, i32, i32, i64, i32] + [vp] * 11 + [i32, i32]
+    L.evr_sg4_plan_create_ex.restype = i32
+    L.evr_sg4_plan_create_ex.argtypes = [C.POINTER(vp), i32, i32, i32, i32, i64, i32] + [vp] * 5 + [i64, i64] + [vp] * 6 + [i32, i32]
+    L.evr_sg4_device_count.restype = i32
     L.evr_sg4_plan_set_op.restype = i32
     L.evr_sg4_plan_set_op.argtypes = [vp, i32, i32, vp, vp, vp, vp, vp]
     L.evr_sg4_plan_set_op10.restype = i32
@@ -84,6 +90,11 @@ def lib():
     L.evr_sg4_apply_device.argtypes = [vp, i32, vp, vp, vp]
     L.evr_sg4_apply_device_scaled.restype = i32
     L.evr_sg4_apply_device_scaled.argtypes = [vp, i32, vp, vp, C.c_double, C.c_double, vp]
+    for name, at in (("evr_sg4_BtoG", [vp, i32, vp, vp]), ("evr_sg4_GtoB", [vp, i32, vp, vp]),
+                     ("evr_sg4_DerivOp_G", [vp, i32, vp, vp, i32, i32]), ("evr_sg4_BtoG_device", [vp, i32, vp, vp, vp]),
+                     ("evr_sg4_GtoB_device", [vp, i32, vp, vp, vp]), ("evr_sg4_DerivOp_G_device", [vp, i32, vp, i32, i32, vp])):
+        getattr(L, name).restype = i32
+        getattr(L, name).argtypes = at
     L.evr_sg4_plan_info.restype = i64
     L.evr_sg4_plan_info.argtypes = [vp, i32]
     L.evr_sg4_plan_destroy.restype = i32
@@ -98,6 +109,25 @@ def lib():
     L.evr_sg4_reduce_to.argtypes = [vp, i32, i64, vp, vp]
     L.evr_sg4_slice_bounds.restype = i32
     L.evr_sg4_slice_bounds.argtypes = [i64, i32, i32, C.POINTER(i64), C.POINTER(i64)]
+    f64 = C.c_double
+    L.evr_sg4_vec_alloc.restype = i32
+    L.evr_sg4_vec_alloc.argtypes = [C.POINTER(vp), i64, i32]
+    L.evr_sg4_vec_free.restype = i32
+    L.evr_sg4_vec_free.argtypes = [vp]
+    L.evr_sg4_vec_upload.restype = i32
+    L.evr_sg4_vec_upload.argtypes = [vp, vp, i64, vp]
+    L.evr_sg4_vec_download.restype = i32
+    L.evr_sg4_vec_download.argtypes = [vp, vp, i64, vp]
+    L.evr_sg4_vec_gram.restype = i32
+    L.evr_sg4_vec_gram.argtypes = [i64, i32, vp, i64, i32, vp, i64, vp, vp]
+    L.evr_sg4_vec_lincomb.restype = i32
+    L.evr_sg4_vec_lincomb.argtypes = [i64, i32, vp, i64, i32, vp, f64, vp, i64, vp]
+    L.evr_sg4_vec_scale.restype = i32
+    L.evr_sg4_vec_scale.argtypes = [i64, f64, vp, vp]
+    L.evr_sg4_vec_precond.restype = i32
+    L.evr_sg4_vec_precond.argtypes = [i64, vp, vp, f64, f64, vp]
+    L.evr_sg4_vec_schmidt.restype = i32
+    L.evr_sg4_vec_schmidt.argtypes = [i64, i32, vp, i64, vp, C.POINTER(f64), vp]
     L.evr_sg4_set_devices.restype = i32
     L.evr_sg4_set_devices.argtypes = [i32]
     L.evr_sg4_get_devices.restype = i32

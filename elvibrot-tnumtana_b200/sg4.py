@@ -160,6 +160,62 @@ class OpGrid:
     Grid: Optional[np.ndarray] = None      # (NQ,nb0,nb0) Fortran order, whole Smolyak grid
 
 
+class SG4Transforms:
+    """Whole-vector transforms of an SG4 basis (nested-SG4 entry): the SparseGrid_type = 4 branches of the reference's
+    RecRvecB_TO_RVecG / RecRVecG_TO_RvecB / DerivOp_TO_RVecG (sub_Basis/sub_module_basis_BtoG_GtoB.f90:831-847, 252-273,
+    1394-1416), batched over the rows of the arguments (the outer index when the SG4 basis sits inside a direct product)."""
+
+    def __init__(self, BasisnD: "SG4Basis", device: int = -1):
+        self.BasisnD = b = BasisnD
+        self._plan = C.c_void_p()
+        _lib.check(_lib.lib().evr_sg4_plan_create(
+            C.byref(self._plan), device, b.D, b.nb_SG, b.nb0, b.nb, b.LG,
+            b.nDind_SmolyakRep_Tab_nDval.ctypes.data, b.WeightSG.ctypes.data,
+            b.tab_nq_OF_SRep.ctypes.data, b.tab_nb_OF_SRep.ctypes.data, b.tab_iB_OF_SRep_TO_iB.ctypes.data,
+            b.nq_of.ctypes.data, b.nb_of.ctypes.data,
+            b.B.ctypes.data, b.BTw.ctypes.data, b.D1.ctypes.data, b.D2.ctypes.data, 0, b.nb_SG), "evr_sg4_plan_create")
+
+    def _rows(self, v, n):
+        v = np.ascontiguousarray(v, dtype=np.float64)
+        one = v.ndim == 1
+        v = v[None, :] if one else v
+        if v.shape[1] != n:
+            raise ValueError(f"vector has {v.shape[1]} entries, expected {n}")
+        return v, one
+
+    def RvecB_TO_RvecG(self, RvecB):
+        b = self.BasisnD
+        x, one = self._rows(RvecB, b.nb * b.nb0)
+        y = np.empty((x.shape[0], b.nqq * b.nb0))
+        _lib.check(_lib.lib().evr_sg4_BtoG(self._plan, x.shape[0], x.ctypes.data, y.ctypes.data), "evr_sg4_BtoG")
+        return y[0] if one else y
+
+    def RvecG_TO_RvecB(self, RvecG):
+        b = self.BasisnD
+        x, one = self._rows(RvecG, b.nqq * b.nb0)
+        y = np.empty((x.shape[0], b.nb * b.nb0))
+        _lib.check(_lib.lib().evr_sg4_GtoB(self._plan, x.shape[0], x.ctypes.data, y.ctypes.data), "evr_sg4_GtoB")
+        return y[0] if one else y
+
+    def DerivOp_TO_RvecG(self, RvecG, mode1: int, mode2: int = 0):
+        b = self.BasisnD
+        x, one = self._rows(RvecG, b.nqq * b.nb0)
+        y = np.empty_like(x)
+        _lib.check(_lib.lib().evr_sg4_DerivOp_G(self._plan, x.shape[0], x.ctypes.data, y.ctypes.data, int(mode1), int(mode2)),
+                   "evr_sg4_DerivOp_G")
+        return y[0] if one else y
+
+    def close(self):
+        if self._plan:
+            _lib.lib().evr_sg4_plan_destroy(C.byref(self._plan))
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class ParamOp:
     """param_Op restricted to what the SG4 action reads; owns the device plan (a pure cache)."""
 

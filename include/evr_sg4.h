@@ -115,6 +115,20 @@ int evr_sg4_plan_create(evr_sg4_plan **plan, int device,
                         const double *B, const double *BTw, const double *D1, const double *D2,
                         int iG_begin, int iG_end);
 
+/* Same, for a caller that only holds a slice of the mapping table: with MPI scheme 1 the reference allocates
+ * tab_iB_OF_SRep_TO_iB(bounds_MPI(1,id):bounds_MPI(2,id)) on rank id (Mapping_table_allocate_MPI,
+ * sub_Basis_SG4/sub_module_basis_BtoG_GtoB_SG4_MPI.f90:62-77).  tab_iB[0] is global entry tab_iB_first (0-based) of the
+ * full table, tab_iB_len entries are valid; they must cover the entries of the terms [iG_begin, iG_end). */
+int evr_sg4_plan_create_ex(evr_sg4_plan **plan, int device,
+                           int D, int nb_SG, int nb0, int64_t nb, int LG,
+                           const int32_t *tab_l, const double *WeightSG,
+                           const int32_t *tab_nq_OF_SRep, const int32_t *tab_nb_OF_SRep,
+                           const int32_t *tab_iB, int64_t tab_iB_first, int64_t tab_iB_len,
+                           const int32_t *nq_of, const int32_t *nb_of,
+                           const double *B, const double *BTw, const double *D1, const double *D2,
+                           int iG_begin, int iG_end);
+int evr_sg4_device_count(void);      /* CUDA devices visible to this process (0 if none): rank -> device maps of MPI callers */
+
 /* Operator description = para_Op%{type_Op, nb_Term, derive_termQdyn, OpGrid(:)}
  * (sub_OpPsi_SG4.f90:1447-1546; term numbering Init_TypeOp,
  * Source_PrimOperator/sub_module_SimpleOp.f90:256-375).
@@ -158,6 +172,27 @@ int evr_sg4_apply_device(evr_sg4_plan *plan, int npsi, const double *d_psi, doub
  * the caller's order; otherwise it is one extra element-wise kernel.  Esc must not be 0. */
 int evr_sg4_apply_device_scaled(evr_sg4_plan *plan, int npsi, const double *d_psi, double *d_Hpsi,
                                 double E0, double Esc, void *cuda_stream);                                               /* device buffers */
+
+/* ---------------------------------------------------------------------------
+ * Whole-vector transforms of the SG4 basis (nested-SG4 entry): what the reference's recursive
+ * RecRvecB_TO_RVecG / RecRVecG_TO_RvecB / DerivOp_TO_RVecG do for SparseGrid_type = 4 when the SG4 basis is a sub-basis of
+ * an outer direct product (sub_Basis/sub_module_basis_BtoG_GtoB.f90:831-847, 252-273, 1394-1416), batched over the outer
+ * index.  They only need the plan (no operator).  Layouts:  RvecB[iv*nb*nb0 + ib0*nb + iB]  (packed basis, as psi);
+ * RvecG[iv*NQ*nb0 + ib0*NQ + q], q over the Smolyak grid of the plan's term range, terms in iG order, first mode
+ * fastest inside a term (SmolyakRep2_TO_tabR1bis, sub_Basis_SG4/sub_module_basis_BtoG_GtoB_SG4.f90:1336-1379).
+ *   BtoG     : tabPackedBasis_TO_SmolyakRepBasis (:1032) + BSmolyakRep_TO[3]_GSmolyakRep (:2216, :2307)
+ *   GtoB     : GSmolyakRep_TO[3]_BSmolyakRep (:2101, :2153) + SmolyakRepBasis_TO_tabPackedBasis (:951): weighted sum over the
+ *              terms (terms with |WeightSG| < 1e-6 skipped, :1004); RvecB is overwritten
+ *   DerivOp_G: DerivOp_TO3_GSmolyakRep (:2583); mode1/mode2 = 1-based SG4 mode owning each index of tab_der
+ *              (Tabder_Qdyn_TO_Qbasis), 0 = none: (k,k) second derivative, (k,l) d/dQ_k d/dQ_l, (k,0) first derivative,
+ *              (0,0) unchanged.  The _device variant works in place.
+ * ------------------------------------------------------------------------- */
+int evr_sg4_BtoG(evr_sg4_plan *plan, int nvec, const double *RvecB, double *RvecG);
+int evr_sg4_GtoB(evr_sg4_plan *plan, int nvec, const double *RvecG, double *RvecB);
+int evr_sg4_DerivOp_G(evr_sg4_plan *plan, int nvec, const double *RvecG_in, double *RvecG_out, int mode1, int mode2);
+int evr_sg4_BtoG_device(evr_sg4_plan *plan, int nvec, const double *d_RvecB, double *d_RvecG, void *cuda_stream);
+int evr_sg4_GtoB_device(evr_sg4_plan *plan, int nvec, const double *d_RvecG, double *d_RvecB, void *cuda_stream);
+int evr_sg4_DerivOp_G_device(evr_sg4_plan *plan, int nvec, double *d_RvecG, int mode1, int mode2, void *cuda_stream);
 
 enum {                           /* 'what' for evr_sg4_plan_info */
     EVR_INFO_LAUNCHES        = 0,   /* kernels launched by this plan so far            */

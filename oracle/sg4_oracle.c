@@ -712,6 +712,104 @@ int orc_tab_oppsi10(int D, int nb_SG, int nb0, int64_t nb, int LG,
     return 0;
 }
 
+/* ------------------------------------------------------------------------
+ * Whole-vector routines of the nested-SG4 entry, one vector at a time, sequential, exactly in the
+ * reference's order of operations.
+ *   mode 0  RvecB -> RvecG :  tabPackedBasis_TO_SmolyakRepBasis  (...BtoG_GtoB_SG4.f90:1032-1105)
+ *                             BSmolyakRep_TO3_GSmolyakRep          (:2307-2383, per term BDP_TO_GDP_OF_SmolyakRep :2385-2496)
+ *                             SmolyakRep2_TO_tabR1bis              (:1336-1379)
+ *   mode 1  RvecG -> RvecB :  tabR2bis_TO_SmolyakRep1              (:1452-1496)
+ *                             GSmolyakRep_TO3_BSmolyakRep          (:2153-2214, per term GDP_TO_BDP_OF_SmolyakRep :2497-2581)
+ *                             SmolyakRepBasis_TO_tabPackedBasis    (:951-1028): tabR = 0, terms with |W| < 1e-6 skipped
+ *   mode 2  RvecG -> RvecG :  DerivOp_TO3_GSmolyakRep              (:2583-2634, per term DerivOp_TO_RDP_OF_SmolaykRep :2690-2795)
+ * der1/der2: 1-based SG4 mode owning each index of tab_der (0 = none).
+ * RvecB[ib0*nb + iB], RvecG[ib0*NQ + q] (q over all terms in iG order, first mode fastest inside a term).
+ * ---------------------------------------------------------------------- */
+int orc_nested(int mode, int D, int nb_SG, int nb0, int64_t nb, int LG,
+               const int *tab_l, const double *W, const int *tab_nq, const int *tab_nb, const int32_t *map,
+               const int *nq_of, const int *nb_of,
+               const double *Bm, const double *BTw, const double *D1, const double *D2,
+               int der1, int der2, const double *in, double *out)
+{
+    const int nT = D * (LG + 1);
+    int64_t *offB = (int64_t *)malloc(sizeof(int64_t) * nT);
+    int64_t *offG = (int64_t *)malloc(sizeof(int64_t) * nT);
+    table_offsets(D, LG, nq_of, nb_of, offB, offG);
+    int64_t NQ = 0, maxn = 1;
+    for (int iG = 0; iG < nb_SG; ++iG) {
+        NQ += tab_nq[iG];
+        int64_t m = 1;
+        for (int k = 0; k < D; ++k) {
+            int l = tab_l[iG * D + k];
+            int a = nq_of[k * (LG + 1) + l], b = nb_of[k * (LG + 1) + l];
+            m *= (a > b) ? a : b;
+        }
+        if (m * nb0 > maxn) maxn = m * nb0;
+    }
+    double *X = (double *)malloc(sizeof(double) * (size_t)maxn), *Y = (double *)malloc(sizeof(double) * (size_t)maxn);
+    if (mode == 1) memset(out, 0, sizeof(double) * (size_t)nb * nb0);                /* tabR(:) = ZERO, :978 */
+    if (mode == 2 && out != in) memcpy(out, in, sizeof(double) * (size_t)NQ * nb0);
+    int64_t off_b = 0, off_q = 0;
+    int tnq[ORC_MAXD], tnb[ORC_MAXD];
+    for (int iG = 0; iG < nb_SG; ++iG) {
+        const int nq = tab_nq[iG], nbT = tab_nb[iG];
+        int64_t ob[ORC_MAXD], og[ORC_MAXD];
+        for (int k = 0; k < D; ++k) {
+            const int i = k * (LG + 1) + tab_l[iG * D + k];
+            tnq[k] = nq_of[i]; tnb[k] = nb_of[i]; ob[k] = offB[i]; og[k] = offG[i];
+        }
+        const int32_t *mp = map + off_b;
+        double *cur = X, *oth = Y;
+        if (mode == 0) {
+            for (int c = 0; c < nb0; ++c)
+                for (int j = 0; j < nbT; ++j) cur[c * nbT + j] = (mp[j] > 0 && mp[j] <= nb) ? in[(int64_t)c * nb + mp[j] - 1] : 0.0;
+            int64_t left = 1, right = (int64_t)nbT * nb0;
+            for (int k = 0; k < D; ++k) {                    /* every mode, also the 1 x 1 ones (:2441-2470) */
+                right /= tnb[k];
+                mode_apply(Bm + ob[k], tnq[k], tnb[k], cur, oth, left, right);
+                double *t = cur; cur = oth; oth = t;
+                left *= tnq[k];
+            }
+            for (int c = 0; c < nb0; ++c)
+                for (int q = 0; q < nq; ++q) out[(int64_t)c * NQ + off_q + q] = cur[c * nq + q];
+        } else if (mode == 1) {
+            if (fabs(W[iG]) >= 1e-6) {                       /* :1004 */
+                for (int c = 0; c < nb0; ++c)
+                    for (int q = 0; q < nq; ++q) cur[c * nq + q] = in[(int64_t)c * NQ + off_q + q];
+                int64_t left = 1, right = (int64_t)nq * nb0;
+                for (int k = 0; k < D; ++k) {
+                    right /= tnq[k];
+                    mode_apply(BTw + ob[k], tnb[k], tnq[k], cur, oth, left, right);
+                    double *t = cur; cur = oth; oth = t;
+                    left *= tnb[k];
+                }
+                for (int c = 0; c < nb0; ++c)
+                    for (int j = 0; j < nbT; ++j)
+                        if (mp[j] > 0 && mp[j] <= nb) out[(int64_t)c * nb + mp[j] - 1] += W[iG] * cur[c * nbT + j];
+            }
+        } else {
+            for (int c = 0; c < nb0; ++c)
+                for (int q = 0; q < nq; ++q) cur[c * nq + q] = out[(int64_t)c * NQ + off_q + q];
+            int64_t left = 1;
+            for (int k = 0; k < D; ++k) {                    /* loop over the modes as the reference does (:2745-2785) */
+                const int hit1 = (der1 == k + 1), hit2 = (der2 == k + 1);
+                if (hit1 || hit2) {
+                    const double *M = (hit1 && hit2) ? D2 + og[k] : D1 + og[k];
+                    const int64_t right = ((int64_t)nq / (left * tnq[k])) * nb0;
+                    mode_apply(M, tnq[k], tnq[k], cur, oth, left, right);
+                    double *t = cur; cur = oth; oth = t;
+                }
+                left *= tnq[k];
+            }
+            for (int c = 0; c < nb0; ++c)
+                for (int q = 0; q < nq; ++q) out[(int64_t)c * NQ + off_q + q] = cur[c * nq + q];
+        }
+        off_b += nbT; off_q += nq;
+    }
+    free(X); free(Y); free(offB); free(offG);
+    return 0;
+}
+
 int orc_max_threads(void)
 {
 #ifdef _OPENMP

@@ -177,5 +177,33 @@ def tab_oppsi10(D, nb_SG, nb0, nb, LG, tab_l, W, tab_nq, tab_nb, mapping, nq_of,
     return Hpsi
 
 
+def nested(mode, D, nb_SG, nb0, nb, LG, tab_l, W, tab_nq, tab_nb, mapping, nq_of, nb_of, B, BTw, D1, D2, vec, der=(0, 0)):
+    """Whole-vector SG4 routines (orc_nested): mode 0 RvecB -> RvecG, 1 RvecG -> RvecB, 2 derivative on the grid.
+    vec[nvec, len]; returns the transformed vectors."""
+    L = lib()
+    L.orc_nested.restype = C.c_int
+    vec = np.ascontiguousarray(vec, dtype=np.float64)
+    if vec.ndim == 1:
+        vec = vec[None, :]
+    c32 = lambda a: np.ascontiguousarray(a, dtype=np.int32)
+    c64 = lambda a: np.ascontiguousarray(a, dtype=np.float64)
+    tab_l, tab_nq, tab_nb, mapping, nq_of, nb_of = map(c32, (tab_l, tab_nq, tab_nb, mapping, nq_of, nb_of))
+    W, B, BTw, D1, D2 = map(c64, (W, B, BTw, D1, D2))
+    NQ = int(tab_nq.sum())
+    lenB, lenG = nb * nb0, NQ * nb0
+    n_in, n_out = (lenB, lenG) if mode == 0 else ((lenG, lenB) if mode == 1 else (lenG, lenG))
+    assert vec.shape[1] == n_in
+    out = np.empty((vec.shape[0], n_out))
+    vp = lambda a: C.c_void_p(a.ctypes.data)
+    for i in range(vec.shape[0]):
+        rc = L.orc_nested(C.c_int(mode), C.c_int(D), C.c_int(nb_SG), C.c_int(nb0), C.c_int64(nb), C.c_int(LG),
+                          vp(tab_l), vp(W), vp(tab_nq), vp(tab_nb), vp(mapping), vp(nq_of), vp(nb_of),
+                          vp(B), vp(BTw), vp(D1), vp(D2), C.c_int(der[0]), C.c_int(der[1]),
+                          C.c_void_p(vec[i].ctypes.data), C.c_void_p(out[i].ctypes.data))
+        if rc != 0:
+            raise RuntimeError(f"orc_nested failed rc={rc}")
+    return out
+
+
 def max_threads() -> int:
     return lib().orc_max_threads()
