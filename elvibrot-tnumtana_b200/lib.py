@@ -25,7 +25,7 @@ EXPORTS = [
     "evr_sg4_tables_build", "evr_sg4_tables_destroy", "evr_sg4_tables_size", "evr_sg4_tables_get",
     "evr_sg4_ini_iGs", "evr_sg4_balanced_iGs",
     "evr_sg4_plan_create", "evr_sg4_plan_create_ex", "evr_sg4_device_count", "evr_sg4_plan_set_op", "evr_sg4_plan_set_op10", "evr_sg4_apply", "evr_sg4_apply_device", "evr_sg4_apply_device_scaled",
-    "evr_sg4_plan_info", "evr_sg4_plan_destroy",
+    "evr_sg4_plan_info", "evr_sg4_plan_destroy", "evr_sg4_model_grid",
     "evr_sg4_BtoG", "evr_sg4_GtoB", "evr_sg4_DerivOp_G", "evr_sg4_BtoG_device", "evr_sg4_GtoB_device", "evr_sg4_DerivOp_G_device",
     "evr_sg4_allreduce_slices", "evr_sg4_allgather_slices", "evr_sg4_reduce_slice", "evr_sg4_reduce_to", "evr_sg4_slice_bounds",
     "evr_sg4_set_devices", "evr_sg4_get_devices", "evr_sg4_host_register", "evr_sg4_host_unregister",
@@ -95,6 +95,8 @@ def lib():
                      ("evr_sg4_GtoB_device", [vp, i32, vp, vp, vp]), ("evr_sg4_DerivOp_G_device", [vp, i32, vp, i32, i32, vp])):
         getattr(L, name).restype = i32
         getattr(L, name).argtypes = at
+    L.evr_sg4_model_grid.restype = i32
+    L.evr_sg4_model_grid.argtypes = [i32, i32, i32, i32, vp, vp, vp, i32, vp, i32, i32, vp]
     L.evr_sg4_plan_info.restype = i64
     L.evr_sg4_plan_info.argtypes = [vp, i32]
     L.evr_sg4_plan_destroy.restype = i32

@@ -141,6 +141,19 @@ def constant_keo_opgrids(D: int, nb0: int, Gdiag, V: Optional[np.ndarray]) -> Li
     return ops
 
 
+def model_potential_device(basis: SG4Basis, model: int, params) -> np.ndarray:
+    """Closed-form model potential on the whole Smolyak grid, evaluated on the GPU (C-ABI evr_sg4_model_grid; the
+    reference fills this grid point by point during its first H|psi>, sub_OpPsi_SG4.f90:2982-3006)."""
+    from . import lib as _lib
+    x = np.concatenate([basis.tab_basisPrimSG[k][L].x for k in range(basis.D) for L in range(basis.LG + 1)]).astype(np.float64)
+    prm = np.ascontiguousarray(params, dtype=np.float64).ravel()
+    V = np.empty(basis.nqq)
+    _lib.check(_lib.lib().evr_sg4_model_grid(model, basis.D, basis.nb_SG, basis.LG, basis.nDind_SmolyakRep_Tab_nDval.ctypes.data,
+                                             basis.nq_of.ctypes.data, x.ctypes.data, len(prm), prm.ctypes.data, 0, basis.nb_SG,
+                                             V.ctypes.data), "evr_sg4_model_grid")
+    return V
+
+
 def henon_heiles(D: int, L: int, LB: Optional[int] = None, iG_range=None, device: int = -1):
     """Henon-Heiles D-dim, SG4 LB=LG=L (LB may differ), Hm nq=nb=1+2L.  Returns (basis, para_H)."""
     LB = L if LB is None else LB

@@ -146,6 +146,16 @@ int evr_sg4_plan_set_op(evr_sg4_plan *plan, int type_Op, int nb_Term,
                         const uint8_t *grid_zero, const uint8_t *grid_cte,
                         const double *Mat_cte, const double *const *grids);
 
+/* Operator-grid construction on the device for closed-form models: the potential on the Smolyak grid of
+ * the terms [iG_begin, iG_end), in the layout of OpGrid(iterm00)%Grid(:) (terms in iG order, first mode fastest), i.e.
+ * what the reference computes point by point during its first H|psi> (Rec_Qact_SG4_with_Tab_iq + get_d0MatOp_AT_Qact,
+ * sub_OpPsi_SG4.f90:2982-3006).  x_tab = concatenation over k (outer), L (inner) of the nq_k(L) grid points of
+ * tab_basisPrimSG(L,k).  model 1: Henon-Heiles, params[0] = lambda (sub_system_HenonHeiles.f:40-47);
+ * model 2: 1/2 sum_i params[i] Q_i^2.  V_host receives sum_iG nq(iG) doubles; pass it to evr_sg4_plan_set_op. */
+int evr_sg4_model_grid(int model, int D, int nb_SG, int LG, const int32_t *tab_l, const int32_t *nq_of,
+                       const double *x_tab, int nparam, const double *params, int iG_begin, int iG_end,
+                       double *V_host);
+
 /* type_Op = 10 with the metric tensor cached per grid point (next row 8f-1 of SURVEY.md):
  *   H psi = -1/2 (Jac sq)^-1 sum_i d_i [ Jac sum_j GG(:,j,i) d_j (sq psi) ] + V psi
  * (sub_OpPsi_SG4.f90:1548-1650).  The reference recomputes GG/Jac/rho with Tnum at every grid point of every

@@ -563,3 +563,20 @@ def test_in_place_call_is_rejected(evr):
     h = np.zeros(basis.nb)
     with pytest.raises(evr.EvrSg4Error, match="overlap"):
         op.apply_host(h, out=h)
+
+
+def test_model_potential_grid_built_on_the_device(evr):
+    """evr_sg4_model_grid against the host evaluation of the same closed-form potentials, point by point in
+    the reference's grid order (first mode fastest, terms in iG order)."""
+    for D, L in [(6, 3), (12, 4), (3, 5)]:
+        basis = evr.workloads.hm_sg4_basis(D, L, L, 1, 2)
+        V_host = evr.workloads.henon_heiles_potential(basis)
+        V_dev = evr.workloads.model_potential_device(basis, 1, [evr.workloads.LAMBDA_HH])
+        assert np.abs(V_dev - V_host).max() <= 1e-13 * max(1.0, np.abs(V_host).max())
+    basis = evr.workloads.hm_sg4_basis(4, 3, 3, 1, 2)
+    k = np.array([1.0, 0.5, 2.0, 0.25])
+    Vh = np.concatenate([evr.workloads._term_outer_sum(basis, iG, lambda kk, x: 0.5 * k[kk] * x * x).ravel(order="F")
+                         for iG in range(basis.nb_SG)])
+    assert np.abs(evr.workloads.model_potential_device(basis, 2, k) - Vh).max() < 1e-13
+    with pytest.raises(evr.EvrSg4Error, match="model"):
+        evr.workloads.model_potential_device(basis, 7, [1.0])
