@@ -813,6 +813,8 @@ extern "C" int evr_sg4_plan_set_op(evr_sg4_plan *p, int type_Op, int nb_Term, co
 {
     if (!p) return fail("evr_sg4_plan_set_op: null plan");
     if (!p->sub.empty()) return evr::multi_set_op(p, type_Op, nb_Term, term_mode, grid_zero, grid_cte, Mat_cte, grids);
+    for (auto &g : p->graphs) cudaGraphExecDestroy(g.exec);      // captured launch sequences belong to the previous operator
+    p->graphs.clear();
     if (type_Op != 0 && type_Op != 1)
         return fail("evr_sg4_plan_set_op: type_Op must be 0 or 1 (use evr_sg4_plan_set_op10 for type_Op=10)");
     if (nb_Term < 1 || !grid_zero || !grid_cte) return fail("evr_sg4_plan_set_op: bad term list");
@@ -909,6 +911,8 @@ extern "C" int evr_sg4_plan_set_op10(evr_sg4_plan *p, int n_act, const int32_t *
 {
     if (!p) return fail("evr_sg4_plan_set_op10: null plan");
     if (!p->sub.empty()) return evr::multi_set_op10(p, n_act, act_mode, V, GG, Jac, sq);
+    for (auto &g : p->graphs) cudaGraphExecDestroy(g.exec);
+    p->graphs.clear();
     if (n_act < 1 || n_act > EVR_MAXD || !act_mode || !GG || !Jac || !sq) return fail("evr_sg4_plan_set_op10: bad arguments");
     CUDA_TRY(cudaSetDevice(p->device));
     const int nb0 = p->nb0;
@@ -976,8 +980,8 @@ __global__ void sg4_permute_out_scaled(const int32_t *__restrict__ perm, const l
 
 struct ScaleArgs { bool on; double E0, Esc; };
 
-static int launch(evr_sg4_plan *p, int npsi, const double *d_psi_user, double *d_Hpsi_user, cudaStream_t st,
-                  const ScaleArgs sc = ScaleArgs{false, 0.0, 1.0})
+static int launch_direct(evr_sg4_plan *p, int npsi, const double *d_psi_user, double *d_Hpsi_user, cudaStream_t st,
+                         const ScaleArgs sc)
 {
     const size_t bytes = (size_t)npsi * p->nb * p->nb0 * sizeof(double);
     const double *d_psi = d_psi_user;
@@ -1065,6 +1069,87 @@ static int launch(evr_sg4_plan *p, int npsi, const double *d_psi_user, double *d
         p->launches += 1;
         CUDA_TRY(cudaGetLastError());
     }
+    return 0;
+}
+
+// ---- CUDA graph of one H|psi> ----------------------------------------------------------------------------------------
+// The per-call launch sequence (permute-in, memset, one kernel per (size class, flavour) on forked streams, joins,
+// permute-out / scaling) is captured once per (npsi, psi, Hpsi, scaling) and replayed with a single cudaGraphLaunch: the
+// small reference shapes (HCN_UT, pyrazine, the 6-D KAT) are bound by that sequence, not by the kernels, and at N > 1 it is
+// the fixed part of every rank's step.  Measured (profiles/r2/sweep12_cuda_graph.txt): 1-5 % on the small shapes, nothing at
+// L = 7, and a Davidson block on the generic kernel (HCN shape, 27 vectors) loses the overlap of its class launches
+// (344 vs 216 us) -- so the graph is opt-in: EVR_SG4_GRAPH=1.
+static int bind_iso_arrays(evr_sg4_plan *p, cudaStream_t st)
+{
+    if (!p->fast) return 0;
+    bool any_v1_iso = false, any_v2_iso = false;
+    for (int c = 0; c < p->n_classes; ++c) if (p->fclass_is_iso[c]) (p->fclass_v2[c] ? any_v2_iso : any_v1_iso) = true;
+    if (any_v1_iso && evr::iso_bind(p->device, p->iso_id, p->iso_blocks.data(), st)) return 1;
+    if (any_v2_iso && evr::v2_iso_bind(p->device, p->iso_id, p->iso_blocks.data(), st)) return 1;
+    return 0;
+}
+
+static int launch(evr_sg4_plan *p, int npsi, const double *d_psi_user, double *d_Hpsi_user, cudaStream_t st,
+                  const ScaleArgs sc = ScaleArgs{false, 0.0, 1.0})
+{
+    static const bool graphs_on = getenv("EVR_SG4_GRAPH") && atoi(getenv("EVR_SG4_GRAPH")) != 0;
+    if (!graphs_on || p->n_terms == 0 || p->stream == nullptr) return launch_direct(p, npsi, d_psi_user, d_Hpsi_user, st, sc);
+    for (auto &g : p->graphs)
+        if (g.npsi == npsi && g.psi == d_psi_user && g.Hpsi == d_Hpsi_user && g.scaled == sc.on && g.E0 == sc.E0 && g.Esc == sc.Esc) {
+            if (bind_iso_arrays(p, st)) return 1;               // another plan may have re-bound the constant arrays
+            CUDA_TRY(cudaGraphLaunch(g.exec, st));
+            p->launches += g.kernels;
+            g.stamp = ++p->graph_clock;
+            return 0;
+        }
+    // first call with these arguments: allocations and bindings happen outside the capture
+    if (p->fast && p->fast_block_order) {
+        const int64_t nvecs = (int64_t)npsi * p->nb0;
+        if (nvecs * p->nb > p->int_cap) {
+            const size_t bytes = (size_t)npsi * p->nb * p->nb0 * sizeof(double);
+            for (auto &g : p->graphs) cudaGraphExecDestroy(g.exec);     // they reference the old internal buffers
+            p->graphs.clear();
+            CUDA_TRY(cudaStreamSynchronize(st));
+            cudaFree(p->d_psi_int); cudaFree(p->d_Hpsi_int); p->d_psi_int = p->d_Hpsi_int = nullptr; p->int_cap = 0;
+            CUDA_TRY(cudaMalloc((void **)&p->d_psi_int, bytes));
+            CUDA_TRY(cudaMalloc((void **)&p->d_Hpsi_int, bytes));
+            p->int_cap = nvecs * p->nb;
+        }
+    }
+    if (bind_iso_arrays(p, st)) return 1;
+    // capture on the plan's own stream (the caller's may be the legacy default stream, which cannot capture)
+    cudaStream_t cs = p->stream;
+    const int64_t l0 = p->launches;
+    if (cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+        cudaGetLastError();
+        return launch_direct(p, npsi, d_psi_user, d_Hpsi_user, st, sc);
+    }
+    const int rc = launch_direct(p, npsi, d_psi_user, d_Hpsi_user, cs, sc);
+    cudaGraph_t graph = nullptr;
+    const cudaError_t ec = cudaStreamEndCapture(cs, &graph);
+    const int kernels = (int)(p->launches - l0);
+    p->launches = l0;
+    if (rc || ec != cudaSuccess || !graph) {
+        if (graph) cudaGraphDestroy(graph);
+        cudaGetLastError();
+        if (rc) return 1;
+        return launch_direct(p, npsi, d_psi_user, d_Hpsi_user, st, sc);
+    }
+    evr_sg4_plan::GraphEntry g;
+    const cudaError_t ei = cudaGraphInstantiate(&g.exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ei != cudaSuccess) { cudaGetLastError(); return launch_direct(p, npsi, d_psi_user, d_Hpsi_user, st, sc); }
+    g.npsi = npsi; g.psi = d_psi_user; g.Hpsi = d_Hpsi_user; g.scaled = sc.on; g.E0 = sc.E0; g.Esc = sc.Esc; g.kernels = kernels;
+    g.stamp = ++p->graph_clock;
+    if (p->graphs.size() >= 8) {                                 // keep the eight most recently used argument sets
+        size_t old = 0;
+        for (size_t i = 1; i < p->graphs.size(); ++i) if (p->graphs[i].stamp < p->graphs[old].stamp) old = i;
+        cudaGraphExecDestroy(p->graphs[old].exec);
+        p->graphs.erase(p->graphs.begin() + old);
+    }
+    p->graphs.push_back(g);
+    CUDA_TRY(cudaGraphLaunch(g.exec, st));
+    p->launches += kernels;
     return 0;
 }
 
@@ -1183,6 +1268,9 @@ extern "C" int evr_sg4_plan_destroy(evr_sg4_plan **pp)
     evr_sg4_plan *p = *pp;
     if (!p->sub.empty()) { evr::multi_destroy(p); delete p; *pp = nullptr; return 0; }
     cudaSetDevice(p->device);
+    cudaDeviceSynchronize();
+    for (auto &g : p->graphs) cudaGraphExecDestroy(g.exec);
+    p->graphs.clear();
     cudaFree(p->d_terms); cudaFree(p->d_lev); cudaFree(p->d_map); cudaFree(p->d_nq_of); cudaFree(p->d_nb_of);
     cudaFree(p->d_offB); cudaFree(p->d_offG); cudaFree(p->d_B); cudaFree(p->d_BTw); cudaFree(p->d_D1); cudaFree(p->d_D2);
     cudaFree(p->d_opterms); cudaFree(p->d_grids); cudaFree(p->d_psi); cudaFree(p->d_Hpsi);

@@ -83,6 +83,10 @@ struct evr_sg4_plan {
     int gclass_threads[4] = {0}, gclass_occ[4] = {0};
     size_t gclass_smem[4] = {0};
     evr::PlanDev pd{};
+    // CUDA graphs of the per-call launch sequence, keyed by the call's arguments (sg4_plan.cu: launch)
+    struct GraphEntry { int npsi; const double *psi; double *Hpsi; bool scaled; double E0, Esc; cudaGraphExec_t exec; int kernels; uint64_t stamp; };
+    std::vector<GraphEntry> graphs;
+    uint64_t graph_clock = 0;
     // multi-device parent (evr_sg4_set_devices, sg4_multi.cu): one sub-plan per device over a share of the term range;
     // a parent owns no device data of its own
     std::vector<evr_sg4_plan *> sub;
