@@ -235,7 +235,7 @@ __device__ __forceinline__ void tile_keo(double (&a)[N2][N1], const double (&v)[
     }
 }
 
-enum { PASS_B2G = 0, PASS_G2B = 1, PASS_LAST = 2, PASS_KEO = 3 };
+enum { PASS_B2G = 0, PASS_G2B = 1, PASS_LAST = 2, PASS_KEO = 3, PASS_G2B_RED = 4 };
 
 struct PassArgs {
     double *psi, *acc;          // shared-memory buffers of this item
@@ -248,6 +248,12 @@ struct PassArgs {
     int hasV;                   // LAST: V of the term sits in the acc buffer
     int fuse_g2b;               // LAST / KEO: also apply BTw of this group before storing acc
     int store_psi;              // LAST: psi needed later (G > 1)
+    // G2B_RED (last G -> B pass scatters from registers): staged gather map, result vector, folded weight, switch
+    const int *smap;
+    double *y;
+    double weight;
+    int nored;
+    int hi_major_ok;            // experiment switch (EVR_SG4_DEBUG bit 256 clears it)
 };
 
 __device__ __forceinline__ int tile_origin(const int t, const int stride, const unsigned magic, const int tile)
@@ -266,12 +272,41 @@ __device__ __forceinline__ void run_pass(const PassArgs &A)
     const double *__restrict__ B1 = (MS == 2) ? c_iso + IsoOff<N1>::value : A.pool + A.m1, *__restrict__ W1 = B1 + NN1, *__restrict__ T1 = B1 + 2 * NN1;
     const double *__restrict__ B2 = (MS == 2) ? c_iso + IsoOff<(N2 > 1 ? N2 : N1)>::value : A.pool + ((N2 > 1) ? A.m2 : A.m1), *__restrict__ W2 = B2 + NN2, *__restrict__ T2 = B2 + 2 * NN2;
     const int stride = S1 ? 1 : A.stride;
+    // Lane -> tile mapping.  Default: consecutive lanes take consecutive positions of the faster dimensions (lo), which
+    // is conflict-free for stride 1 (odd tile sizes) and for stride >= 16.  For 1 < stride < 16 the 16 lanes of a
+    // shared-memory wavefront wrap around lo and collide (ncu, round 2: 31 % of the wavefronts were bank conflicts); there
+    // consecutive lanes walk the SLOWER dimensions instead (hi fastest): their addresses differ by stride*TILE doubles,
+    // an odd number for the odd mode sizes 1+2L, i.e. 16 different bank pairs.  The scattering pass keeps the default
+    // (its lanes must cover runs of consecutive entries).
+    const int nhi = S1 ? 0 : ntiles / max(stride, 1);
+    const bool hi_major = !S1 && KIND != PASS_G2B_RED && A.hi_major_ok && stride > 1 && stride < 16 && nhi > 1 && ((stride * TILE) & 1);
+    const unsigned mg_hi = hi_major ? 0xFFFFFFFFu / (unsigned)nhi + 1u : 0u;
     for (int c = 0; c < A.nb0; ++c) {
         double *__restrict__ psi = A.psi + c * A.nq, *__restrict__ acc = A.acc + c * A.nq;
         for (int t = A.tid; t < ntiles; t += A.nthr) {
-            const int q0 = tile_origin(t, stride, A.magic, TILE);
+            int q0;
+            if (hi_major) {
+                const int lo = (int)__umulhi((unsigned)t, mg_hi);
+                q0 = lo + stride * TILE * (t - lo * nhi);
+            } else q0 = tile_origin(t, stride, A.magic, TILE);
             double v[N2][N1];
-            if (KIND == PASS_B2G) {
+            if (KIND == PASS_G2B_RED) {
+                // last G -> B pass: transform, then weighted scatter-add straight from registers through the staged map
+                int m[N2][N1];
+#pragma unroll
+                for (int j = 0; j < N2; ++j)
+#pragma unroll
+                    for (int i = 0; i < N1; ++i) m[j][i] = A.smap[q0 + stride * (i + N1 * j)];
+                tile_load<N1, N2>(v, acc + q0, stride);
+                tile_xform<N1, N2, MS>(v, W1, W2);
+                if (!A.nored) {
+#pragma unroll
+                    for (int j = 0; j < N2; ++j)
+#pragma unroll
+                        for (int i = 0; i < N1; ++i)
+                            if (m[j][i] >= 0) atomicAdd(A.y + m[j][i], A.weight * v[j][i]);
+                }
+            } else if (KIND == PASS_B2G) {
                 tile_load<N1, N2>(v, psi + q0, stride);
                 tile_xform<N1, N2, MS>(v, B1, B2);
                 tile_store<N1, N2>(v, psi + q0, stride);
@@ -530,18 +565,18 @@ __device__ __forceinline__ void dispatch_pass(const int tmpl, const int n1, cons
         case 21: if constexpr (TRI) run_pass<3, 7, KIND, MS, HV, FG, SP, S1>(A); break;
         case 22: if constexpr (TRI) run_pass<3, 9, KIND, MS, HV, FG, SP, S1>(A); break;
         case 23: if constexpr (TRI) run_pass<5, 5, KIND, MS, HV, FG, SP, S1>(A); break;
-        case EVR_TMPL_CUBE3: if constexpr (TRI) run_pass_cube<3, KIND, MS, HV, SP, S1>(A); break;
+        case EVR_TMPL_CUBE3: if constexpr (TRI && KIND != PASS_G2B_RED) run_pass_cube<3, KIND, MS, HV, SP, S1>(A); break;
         default: break;          // unreachable: the plan sends terms with other mode sizes to the pool-based instantiations
         }
     } else if (RT) {             // terms with a mode size that has no template: runtime-size single-mode tiles only
-        run_pass_rt<MS>(A, KIND, n1);
+        if constexpr (KIND != PASS_G2B_RED) run_pass_rt<MS>(A, KIND, n1);
     } else {
         switch (tmpl) {
 #define X(id, a, b) case id: run_pass<a, b, KIND, MS, HV, FG, SP>(A); break;
             EVR_TMPL_LIST(X)
 #undef X
-        case EVR_TMPL_CUBE3: if (TRI) run_pass_cube<3, KIND, MS, HV, SP>(A); break;
-        case EVR_TMPL_CUBE2: if (TRI) run_pass_cube<2, KIND, MS, HV, SP>(A); break;
+        case EVR_TMPL_CUBE3: if constexpr (TRI && KIND != PASS_G2B_RED) run_pass_cube<3, KIND, MS, HV, SP>(A); break;
+        case EVR_TMPL_CUBE2: if constexpr (TRI && KIND != PASS_G2B_RED) run_pass_cube<2, KIND, MS, HV, SP>(A); break;
         default: break;          // unreachable: the plan sends such terms to the RT instantiation
         }
     }
@@ -742,6 +777,8 @@ sg4_term_kernel_fast(const FastPlanDev P, const FastClassDev Cc, const int npsi,
             PassArgs A;
             A.psi = s_psi; A.acc = s_acc; A.nq = nq; A.nb0 = nb0; A.vshift = T->vshift; A.tid = tid; A.nthr = gsize;
             A.hasV = 0; A.fuse_g2b = 0; A.store_psi = 0; A.pool = mats;
+            A.smap = reinterpret_cast<const int *>(s_psi); A.y = y; A.weight = T->weight; A.nored = (P.dbg & 8) ? 1 : 0;
+            A.hi_major_ok = (P.dbg & 256) ? 0 : 1;
             auto set_group = [&](int g) {
                 const FastGroup &Gr = T->g[g];
                 A.stride = Gr.stride; A.magic = Gr.magic; A.m1 = Gr.mat1; A.m2 = Gr.mat2; A.m3 = Gr.mat3;
@@ -749,7 +786,12 @@ sg4_term_kernel_fast(const FastPlanDev P, const FastClassDev Cc, const int npsi,
             // once the last pass that reads the psi buffer is done, the sorted scatter map (4 B/entry) and the positions
             // (2 B/entry) of the term stream into that buffer while the remaining G -> B passes run
             const int nq32 = (nq + 31) & ~31;
-            const bool local_scatter = (P.dbg & 128) != 0 && nb0 == 1;
+            // The last G -> B pass scatters from registers (no sorted map, no positions, no scatter loop) when it works on a
+            // plain tile of the slowest group, whose consecutive lanes cover runs of >= 8 consecutive entries; the map it
+            // needs is the gather map, staged again (4 bytes per entry) while the kinetic passes run.
+            const bool fused_red = nb0 == 1 && !RT && G >= 2 && T->g[G - 1].n3 == 0 && T->g[0].n3 == 0 && T->g[G - 1].stride >= 8 &&
+                                   !(P.dbg & 512) && P.stage == nullptr;
+            const bool local_scatter = ((P.dbg & 128) != 0 && nb0 == 1) || fused_red;
             auto stage_scatter_map = [&]() {          // called behind a group barrier: nobody reads the psi buffer any more
                 if (tid == 0) {
                     char *dst = reinterpret_cast<char *>(s_psi);
@@ -830,7 +872,11 @@ sg4_term_kernel_fast(const FastPlanDev P, const FastClassDev Cc, const int npsi,
                 const int g_first = (T->g[0].n3 > 0) ? 0 : ((G == 1) ? (v_fused ? 1 : 0) : 1);
                 for (int g = g_first; g < G; ++g) {
                     set_group(g);
-                    if (MS == 2 && g == 0) dispatch_pass<PASS_G2B, MS, RT, TRI, false, false, false, MS == 2>(T->g[g].tmpl, T->g[g].n1, A);
+                    if (fused_red && g == G - 1) {
+                        mbar_wait(s_bar, ph_map); ph_map ^= 1;          // the staged map has landed
+                        dispatch_pass<PASS_G2B_RED, MS, RT, TRI, false, false, false>(T->g[g].tmpl, T->g[g].n1, A);
+                    }
+                    else if (MS == 2 && g == 0) dispatch_pass<PASS_G2B, MS, RT, TRI, false, false, false, MS == 2>(T->g[g].tmpl, T->g[g].n1, A);
                     else dispatch_pass<PASS_G2B, MS, RT, TRI, false, false, false>(T->g[g].tmpl, T->g[g].n1, A);
                     group_sync(gsize, group);
                 }
@@ -838,7 +884,7 @@ sg4_term_kernel_fast(const FastPlanDev P, const FastClassDev Cc, const int npsi,
             // weighted scatter-add (tabR_AT_iG_TO_tabPackedBasis): sorted entries, one per lane (neighbouring lanes ->
             // neighbouring addresses, the FP64 reductions of a warp share L2 sectors); map and positions come from the
             // staged copy in the psi buffer; padding / dropped entries carry index -1
-            {
+            if (!fused_red) {
                 mbar_wait(s_bar, ph_map); ph_map ^= 1;      // (the barrier behind the last pass made acc visible)
                 const double weight = T->weight;
                 const int *s_map = reinterpret_cast<const int *>(s_psi);
@@ -847,6 +893,14 @@ sg4_term_kernel_fast(const FastPlanDev P, const FastClassDev Cc, const int npsi,
                 // software-pipelined by hand (the entry of the next round is loaded before this round's reduction is
                 // issued); an unrolled loop would need the trip count, i.e. a division by the runtime group size
                 int j = tid;
+                if (P.stage) {          // deterministic mode: stage the weighted entries, no reductions
+                    double *sg = P.stage + (long long)ip * nb0 * P.stage_ld + T->map_off;
+                    for (; j < nq32; j += gsize) {
+                        const int mm = s_map[j], qq = local_scatter ? j : (int)s_pos[j];
+                        if (mm >= 0)
+                            for (int c = 0; c < nb0; ++c) sg[(long long)c * P.stage_ld + j] = weight * s_acc[c * nq + qq];
+                    }
+                }
                 int m = (j < nq32) ? s_map[j] : -1, q = (j < nq32) ? (local_scatter ? j : (int)s_pos[j]) : 0;
                 while (j < nq32) {
                     const int jn = j + gsize;

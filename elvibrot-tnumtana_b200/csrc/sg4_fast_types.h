@@ -52,6 +52,10 @@ struct FastPlanDev {
     const uint16_t *pos;    // per term: term-local position (internal layout) of each sorted entry
     const double *mats;     // pool of [B|BTw|T] blocks
     const double *V;        // [nb0*nb0][NQ_local] permuted to the internal layout
+    // deterministic mode (EVR_SG4_DETERMINISTIC=1): the scatter writes every weighted entry to stage[(rhs*nb0+c)*stage_ld + entry]
+    // instead of an FP64 reduction; a second kernel sums the entries of every packed element in a fixed order
+    double *stage;
+    long long stage_ld;
 };
 
 

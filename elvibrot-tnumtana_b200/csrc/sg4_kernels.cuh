@@ -65,6 +65,9 @@ struct PlanDev {
     int n_plain, n_sweeps;
     int sweep_mode[EVR_MAXD];
     int sweep_begin[EVR_MAXD + 1];
+    // deterministic mode: see FastPlanDev (entry = position in the plan's mapping slice)
+    double *stage;
+    long long stage_ld;
 };
 
 // ---- division by a per-term constant: q / d = umulhi(q, magic(d)) --------------------------------
@@ -325,6 +328,12 @@ sg4_term_kernel_generic(const PlanDev P, const GenClassDev Cc, const int npsi,
                 }
             }
             // ---- weighted scatter-add
+            if (P.stage) {
+                double *sg = P.stage + (long long)ip * nb0 * P.stage_ld + T.map_off;
+                for (int j = threadIdx.x; j < nbT; j += blockDim.x)
+                    if (mp[j] > 0)
+                        for (int c = 0; c < nb0; ++c) sg[(long long)c * P.stage_ld + j] = T.wfold * cur[c * nbT + j];
+            } else
             for (int j = threadIdx.x; j < nbT; j += blockDim.x) {
                 const int m = mp[j];
                 if (m > 0)
@@ -332,6 +341,29 @@ sg4_term_kernel_generic(const PlanDev P, const GenClassDev Cc, const int npsi,
                         atomicAdd(y + (long long)c * P.nb + (m - 1), T.wfold * cur[c * nbT + j]);
             }
             __syncthreads();
+        }
+    }
+}
+
+// deterministic mode: out[v*nb + i] = sum of the staged entries of packed element i in a fixed order.  One warp per
+// element (the lists are very uneven: the lowest basis functions belong to every Smolyak term): lane L adds the entries
+// k = L, L+32, ... in order, then a fixed shuffle tree combines the 32 partial sums.
+static __global__ void __launch_bounds__(256)
+sg4_collect_kernel(const long long nb, const int nvec, const long long *__restrict__ off,
+                   const int32_t *__restrict__ ent, const double *__restrict__ stage, const long long stage_ld,
+                   double *__restrict__ out)
+{
+    const int lane = threadIdx.x & 31;
+    const long long warp0 = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5, nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long i = warp0; i < nb; i += nwarps) {
+        const long long k0 = off[i], k1 = off[i + 1];
+        for (int v = 0; v < nvec; ++v) {
+            const double *sg = stage + (long long)v * stage_ld;
+            double s = 0.0;
+            for (long long k = k0 + lane; k < k1; k += 32) s += sg[ent[k]];
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(0xFFFFFFFFu, s, d);
+            if (lane == 0) out[(long long)v * nb + i] = s;
         }
     }
 }

@@ -34,6 +34,9 @@ using evr::fail;
 extern "C" int evr_sg4_version(void) { return 100; }
 extern "C" const char *evr_sg4_last_error(void) { return evr::g_err.c_str(); }
 
+// deterministic mode: entry lists per packed element from a mapping array (value = 0-based packed index, < 0: none)
+static int build_entry_lists(evr_sg4_plan *p, const std::vector<int32_t> &map0, int64_t n_entries);
+
 template <class T>
 static int upload(T **dptr, const T *h, size_t n)
 {
@@ -165,6 +168,7 @@ int evr::plan_create_single(evr_sg4_plan **out, int device,
     p->device = device; p->D = D; p->nb_SG = nb_SG; p->nb0 = nb0; p->nb = nb; p->LG = LG;
     p->iG_begin = iG_begin; p->iG_end = iG_end; p->n_terms = iG_end - iG_begin;
     p->sm_count = prop.multiProcessorCount;
+    p->deterministic = getenv("EVR_SG4_DETERMINISTIC") && atoi(getenv("EVR_SG4_DETERMINISTIC")) != 0;
     const int nT = D * (LG + 1);
     p->h_nq_of.assign(nq_of, nq_of + nT);
     p->h_nb_of.assign(nb_of, nb_of + nT);
@@ -609,7 +613,7 @@ static int build_fast_path(evr_sg4_plan *p, int nb_Term, const int32_t *term_mod
     // size share their 1-D basis (iso flavour: the kernel ignores the matrix offsets); otherwise only terms on modes with
     // identical matrices do.  The batch capacity adapts to the problem size so that small grids still fill the GPU.
     // second-generation kernel (sg4_fast2.cuh): single channel, iso tiles or pool-in-shared-memory tiles
-    const bool v2_on = nb0 == 1 && envi("EVR_SG4_V2", 0) != 0;   // experimental, off by default
+    const bool v2_on = nb0 == 1 && envi("EVR_SG4_V2", 0) != 0 && !p->deterministic;   // experimental, off by default
     auto flavour_v2 = [&](int fl) { return v2_on && ((fl == 3 && iso && !iso_big) || (fl == 0 && pool_in_smem)); };
     auto term_is_iso = [&](int t) { const int fl = flavour_of(t); return iso && (fl == 3 || (fl == 2 && iso_big)); };
     const int64_t bcap_max = std::max(1, envi("EVR_SG4_BCAP", v2_on ? 3700 : 2350));                   // doubles per psi/acc buffer
@@ -784,6 +788,7 @@ static int build_fast_path(evr_sg4_plan *p, int nb_Term, const int32_t *term_mod
     p->d_fterms = nullptr; p->d_fmap = nullptr; p->d_fmats = nullptr; p->d_fV = nullptr;
     if (upload(&p->d_fterms, fterms.data(), fterms.size())) return 1;
     if (upload(&p->d_fmap, fmap.data(), fmap.size())) return 1;
+    if (p->deterministic && build_entry_lists(p, fmap, NQ_pad)) return 1;   // entries = sorted scatter map positions
     cudaFree(p->d_gmap); p->d_gmap = nullptr;
     if (upload(&p->d_gmap, gmap.data(), gmap.size())) return 1;
     cudaFree(p->d_fpos); p->d_fpos = nullptr; cudaFree(p->d_perm); p->d_perm = nullptr;
@@ -804,6 +809,21 @@ static int build_fast_path(evr_sg4_plan *p, int nb_Term, const int32_t *term_mod
     f.nb = p->nb; f.NQ_local = NQ_pad;      // channel stride of the padded V array
     f.terms = p->d_fterms; f.gmap = p->d_gmap; f.map = p->d_fmap; f.pos = p->d_fpos; f.mats = p->d_fmats; f.V = p->d_fV;
     p->fast = true;
+    return 0;
+}
+
+static int build_entry_lists(evr_sg4_plan *p, const std::vector<int32_t> &map0, int64_t n_entries)
+{
+    std::vector<long long> off((size_t)p->nb + 1, 0);
+    for (int64_t e = 0; e < n_entries; ++e) if (map0[e] >= 0) ++off[map0[e] + 1];
+    for (int64_t i = 0; i < p->nb; ++i) off[i + 1] += off[i];
+    std::vector<int32_t> ent((size_t)std::max<long long>(off[p->nb], 1));
+    std::vector<long long> at(off.begin(), off.end() - 1);
+    for (int64_t e = 0; e < n_entries; ++e) if (map0[e] >= 0) ent[at[map0[e]]++] = (int32_t)e;   // ascending entry order
+    cudaFree(p->d_det_off); cudaFree(p->d_det_ent); p->d_det_off = nullptr; p->d_det_ent = nullptr;
+    if (upload(&p->d_det_off, off.data(), off.size())) return 1;
+    if (upload(&p->d_det_ent, ent.data(), ent.size())) return 1;
+    p->stage_ld = std::max<int64_t>(n_entries, 1);
     return 0;
 }
 
@@ -901,6 +921,11 @@ extern "C" int evr_sg4_plan_set_op(evr_sg4_plan *p, int type_Op, int nb_Term, co
     }
     p->flops_npsi1 += deriv_flops * nb0;
     if (build_fast_path(p, nb_Term, term_mode, grid_zero, grid_cte, Mat_cte, grids)) return 1;
+    if (p->deterministic && !p->fast) {                      // generic kernel: entries = positions of the mapping slice
+        std::vector<int32_t> map0(p->h_map.size());
+        for (size_t e = 0; e < map0.size(); ++e) map0[e] = p->h_map[e] - 1;
+        if (build_entry_lists(p, map0, (int64_t)map0.size())) return 1;
+    }
     p->op_set = true;
     return 0;
 }
@@ -1000,6 +1025,18 @@ static int launch_direct(evr_sg4_plan *p, int npsi, const double *d_psi_user, do
         p->launches += 1;
         d_psi = p->d_psi_int; d_Hpsi = p->d_Hpsi_int;
     }
+    const bool det = p->deterministic && !p->op10 && p->d_det_off != nullptr && p->n_terms > 0;
+    if (det) {
+        const int64_t vecs = (int64_t)npsi * p->nb0;
+        if (vecs > p->stage_vecs) {
+            CUDA_TRY(cudaStreamSynchronize(st));
+            cudaFree(p->d_stage); p->d_stage = nullptr; p->stage_vecs = 0;
+            CUDA_TRY(cudaMalloc((void **)&p->d_stage, (size_t)vecs * p->stage_ld * sizeof(double)));
+            p->stage_vecs = vecs;
+        }
+    }
+    p->fpd.stage = det ? p->d_stage : nullptr; p->fpd.stage_ld = p->stage_ld;
+    p->pd.stage = det ? p->d_stage : nullptr;  p->pd.stage_ld = p->stage_ld;
     CUDA_TRY(cudaMemsetAsync(d_Hpsi, 0, bytes, st));                 // reference zeroes OpPsi (:765)
     if (p->n_terms > 0) {
         if (p->fast) {
@@ -1051,6 +1088,12 @@ static int launch_direct(evr_sg4_plan *p, int npsi, const double *d_psi_user, do
             }
         }
         CUDA_TRY(cudaGetLastError());
+        if (det) {      // fixed-order sums of the staged entries (all class kernels have joined the stream)
+            const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>((p->nb + 7) / 8, 148 * 16));   // one warp per packed element
+            evr::sg4_collect_kernel<<<blocks, 256, 0, st>>>(p->nb, (int)(npsi * p->nb0), p->d_det_off, p->d_det_ent, p->d_stage, p->stage_ld, d_Hpsi);
+            p->launches += 1;
+            CUDA_TRY(cudaGetLastError());
+        }
     }
     if (use_int) {
         const int64_t nvecs = (int64_t)npsi * p->nb0;
@@ -1277,6 +1320,7 @@ extern "C" int evr_sg4_plan_destroy(evr_sg4_plan **pp)
     cudaFree(p->d_fterms); cudaFree(p->d_fmap); cudaFree(p->d_fmats); cudaFree(p->d_fV);
     cudaFree(p->d_fpos); cudaFree(p->d_gmap); cudaFree(p->d_perm); cudaFree(p->d_psi_int); cudaFree(p->d_Hpsi_int);
     cudaFree(p->d_GG); cudaFree(p->d_Jac); cudaFree(p->d_sq);
+    cudaFree(p->d_det_off); cudaFree(p->d_det_ent); cudaFree(p->d_stage);
     if (p->stream) cudaStreamDestroy(p->stream);
     for (int c = 0; c < EVR_MAX_FCLASSES; ++c) { if (p->side[c]) cudaStreamDestroy(p->side[c]); if (p->ev_join[c]) cudaEventDestroy(p->ev_join[c]); }
     if (p->ev_fork) cudaEventDestroy(p->ev_fork);

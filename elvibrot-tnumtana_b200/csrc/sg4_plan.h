@@ -83,6 +83,12 @@ struct evr_sg4_plan {
     int gclass_threads[4] = {0}, gclass_occ[4] = {0};
     size_t gclass_smem[4] = {0};
     evr::PlanDev pd{};
+    // deterministic mode (EVR_SG4_DETERMINISTIC=1 when the plan is created): staged scatter + ordered collection
+    bool deterministic = false;
+    long long *d_det_off = nullptr;          // [nb+1] entry-list offsets per packed element (internal order on the fast path)
+    int32_t *d_det_ent = nullptr;            // entry positions, grouped by packed element, ascending
+    double *d_stage = nullptr;
+    int64_t stage_ld = 0, stage_vecs = 0;
     // CUDA graphs of the per-call launch sequence, keyed by the call's arguments (sg4_plan.cu: launch)
     struct GraphEntry { int npsi; const double *psi; double *Hpsi; bool scaled; double E0, Esc; cudaGraphExec_t exec; int kernels; uint64_t stamp; };
     std::vector<GraphEntry> graphs;

@@ -580,3 +580,31 @@ def test_model_potential_grid_built_on_the_device(evr):
     assert np.abs(evr.workloads.model_potential_device(basis, 2, k) - Vh).max() < 1e-13
     with pytest.raises(evr.EvrSg4Error, match="model"):
         evr.workloads.model_potential_device(basis, 7, [1.0])
+
+
+@pytest.mark.parametrize("case", ["hh12d_L4_fast", "hh12d_L4_block_order", "pyrazine_nb0_2", "hcn_generic"])
+def test_deterministic_mode_is_bit_reproducible(evr, monkeypatch, case):
+    """EVR_SG4_DETERMINISTIC=1: the scatter stages every weighted entry and a second kernel sums the entries of
+    each packed element in a fixed order -- repeated calls are bit-identical and still match the oracle."""
+    monkeypatch.setenv("EVR_SG4_DETERMINISTIC", "1")
+    if case == "hh12d_L4_block_order":
+        monkeypatch.setenv("EVR_SG4_BLOCK_ORDER", "1")
+    if case.startswith("hh12d"):
+        basis, op = evr.workloads.henon_heiles(12, 4)
+        npsi = 2
+    elif case == "pyrazine_nb0_2":
+        basis, op = evr.workloads.pyrazine_12d(2)
+        npsi = 2
+    else:
+        basis = evr.workloads.hm_sg4_basis(3, 4, 5, [10, 1, 1], [10, 2, 2])
+        op = evr.workloads.synthetic_curvilinear(basis)
+        npsi = 3
+    psi = random_psi(basis.nb * basis.nb0, npsi, 5)
+    a = op.apply_host(psi).copy()
+    for _ in range(3):
+        assert np.array_equal(op.apply_host(psi), a)
+    op2 = evr.ParamOp(basis, op.type_Op, op.OpGrid, mode_of_Qact=op.mode_of_Qact)      # a second plan gives the same bits
+    assert np.array_equal(op2.apply_host(psi), a)
+    ref = oracle_apply(op, psi)
+    for i in range(npsi):
+        assert rel_l2(a[i], ref[i]) < TOL
