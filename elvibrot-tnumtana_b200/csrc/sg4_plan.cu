@@ -454,10 +454,11 @@ static int build_fast_path(evr_sg4_plan *p, int nb_Term, const int32_t *term_mod
     // The membership signature is a sum of per-term 64-bit hashes; no multi-index table is needed.
     // The two permutation kernels cost ~12 us per H|psi>, so small problems keep the caller's order (identity
     // permutation, term entries still sorted by address); EVR_SG4_BLOCK_ORDER=0/1 overrides the size heuristic.
-    // The heuristic keys on the size of the WHOLE Smolyak grid, so that every rank of a term-parallel run uses the
-    // same layout as the single-GPU plan.
+    // Measured at HH-12D L=7 on 1/2/4/8 GPUs (profiles/r2/scale_r2_first.txt): the block order pays down to ~6 M grid points
+    // per rank (N <= 4) and costs 17 us of 183 us at N = 8 (3 M points per rank), where the two permutation kernels over the
+    // full vector no longer amortise -- hence the threshold on the points of THIS plan's term range.
     std::vector<int32_t> inv_perm((size_t)p->nb), perm((size_t)p->nb);
-    bool block_order = p->NQ_total >= 8000000;
+    bool block_order = p->NQ_local >= 4000000;
     if (getenv("EVR_SG4_BLOCK_ORDER")) block_order = atoi(getenv("EVR_SG4_BLOCK_ORDER")) != 0;
     p->fast_block_order = block_order;
     if (!block_order) {
