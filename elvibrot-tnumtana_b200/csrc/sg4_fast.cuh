@@ -583,7 +583,7 @@ __device__ __forceinline__ void dispatch_pass(const int tmpl, const int n1, cons
 }
 
 // ---- the kernel ----------------------------------------------------------------------------------
-// One persistent CTA per SM with up to 768 threads, split into thread groups of gsize = 32/64/128
+// One persistent CTA per SM with up to EVR_FAST_MAX_THREADS (512) threads, split into thread groups of gsize = 32/64/128
 // threads; every group owns one Smolyak term at a time (static round-robin over the cost-sorted terms
 // of its size class) and synchronises only with itself (named barriers / __syncwarp).  Global-memory
 // latency of one group's gather/scatter is hidden by the arithmetic of the other groups on the SM;
@@ -683,21 +683,35 @@ sg4_term_kernel_fast(const FastPlanDev P, const FastClassDev Cc, const int npsi,
     // (32-bit item arithmetic, and no division at all for a single right-hand side: a 64-bit divide per item is a
     // ~100-instruction subroutine on the dependent chain of every term)
     const int n_items = Cc.n_terms * npsi;
-    const int w_first = blockIdx.x * ngrp + group;
     auto term_of = [&](const int w) { return (npsi == 1) ? w : (int)((unsigned)w / (unsigned)npsi); };
-    if (w_first < n_items) {   // first descriptor of this group
-        const double *src = reinterpret_cast<const double *>(terms + term_of(w_first));
+    // Work distribution: the items are sorted by cost (largest first); the thread groups of all CTAs draw them from one
+    // counter per launch (list scheduling: every group ends within one item of the others, where the static round-robin
+    // left a tail of up to one item in ~11).  The index is fetched two items ahead, so that the atomic's round trip and the
+    // descriptor copy of the next item overlap the current one.  Cc.counter == nullptr: static round-robin.
+    int *s_w = reinterpret_cast<int *>(s_bar + 2);
+    const bool dyn = Cc.counter != nullptr;
+    int w = blockIdx.x * ngrp + group;
+    if (dyn) {
+        if (tid == 0) { s_w[0] = atomicAdd(Cc.counter, 1); s_w[1] = atomicAdd(Cc.counter, 1); }
+        group_sync(gsize, group);
+        w = s_w[0];
+    }
+    if (w < n_items) {   // first descriptor of this group
+        const double *src = reinterpret_cast<const double *>(terms + term_of(w));
         double *dst = reinterpret_cast<double *>(s_T0);
         for (int i = tid; i < (int)(sizeof(FastTermDev) / 8); i += gsize) cp_async8(dst + i, src + i);
     }
-    int ts = 0;
-    for (int w = w_first; w < n_items; w += step, ts ^= 1) {
+    int ts = 0, w_next = 0;
+    for (; w < n_items; w = w_next, ts ^= 1) {
         const int it = term_of(w);
         const int ip = w - it * npsi;
         cp_async_commit_wait_all();            // descriptor of this item has landed (issued one item ago)
         group_sync(gsize, group);
-        if (w + step < n_items) {              // descriptor of the next item -> other slot, asynchronously
-            const double *src = reinterpret_cast<const double *>(terms + term_of(w + step));
+        w_next = dyn ? s_w[ts ^ 1] : w + step;
+        int w_pend = 0;
+        if (dyn && tid == 0) w_pend = atomicAdd(Cc.counter, 1);      // index of the item after next; stored at the end of this item
+        if (w_next < n_items) {                // descriptor of the next item -> other slot, asynchronously
+            const double *src = reinterpret_cast<const double *>(terms + term_of(w_next));
             double *dst = reinterpret_cast<double *>(s_T0 + (ts ^ 1));
             for (int i = tid; i < (int)(sizeof(FastTermDev) / 8); i += gsize) cp_async8(dst + i, src + i);
         }
@@ -914,6 +928,7 @@ sg4_term_kernel_fast(const FastPlanDev P, const FastClassDev Cc, const int npsi,
                     m = mn; q = qn; j = jn;
                 }
             }
+            if (dyn && tid == 0) s_w[ts] = w_pend;
             group_sync(gsize, group);
         }
     }

@@ -9,7 +9,7 @@ namespace evr {
 
 #define EVR_MAXG 8          // max groups (<= 16 active modes) per term on the fast path
 #define EVR_MAX_FCLASSES 16 // (size class, kernel flavour) pairs = launches per H|psi> on the fast path
-#define EVR_FAST_MBAR_BYTES 16 // two mbarriers per thread group (bulk copies of the map / V slices)
+#define EVR_FAST_MBAR_BYTES 32 // per thread group: two mbarriers (bulk copies of the map / V slices) + two work-item indices
 #define EVR_RT_NMAX 16      // runtime-size single-mode tiles keep up to 16 values in registers
 
 struct FastGroup {
@@ -39,6 +39,7 @@ struct FastClassDev {       // one launch per size class: terms [term_begin, ter
     int tri;                // 1: terms with three-mode cube tiles (TRI instantiation, 512 threads)
     int cap;                // doubles per psi/acc buffer (max nq*nb0 of the class)
     int cta_threads;        // threads per CTA = groups per CTA * gsize (<= 768)
+    int *counter;           // work counter of this launch (zeroed before it); nullptr: static round-robin over the items
 };
 
 struct FastPlanDev {
@@ -68,7 +69,12 @@ struct FastPlanDev {
 #define EVR_TMPL_CUBE3 30    // template id of the 3x3x3 cube tile (only in the TRI instantiation of the kernel)
 #define EVR_TMPL_CUBE2 31    // 2x2x2
 
-#define EVR_FAST_MAX_THREADS 768
+// 512 threads per CTA = 128 registers per thread: the tile passes compile without spills (768 threads / 80 registers:
+// 140-870 bytes of spill traffic per thread that misses the ~6 KB of L1 left beside 222 KB of shared memory; measured
+// 0.398 ms at 768, 0.375 at 640 / 96 registers, 0.361 at 512, profiles/r2/sweep16_threads_per_cta.txt)
+#ifndef EVR_FAST_MAX_THREADS
+#define EVR_FAST_MAX_THREADS 512
+#endif
 #define EVR_FAST_MAX_THREADS_TRI 512   // cube tiles keep 27 values + a 3x3 matrix in registers: 128 registers per thread
 #define EVR_ISO_MAX_THREADS 512        // iso kernel: 128 registers per thread (two 27-value tiles in the fused passes)
 

@@ -617,7 +617,7 @@ static int build_fast_path(evr_sg4_plan *p, int nb_Term, const int32_t *term_mod
     const bool v2_on = nb0 == 1 && envi("EVR_SG4_V2", 0) != 0 && !p->deterministic;   // experimental, off by default
     auto flavour_v2 = [&](int fl) { return v2_on && ((fl == 3 && iso && !iso_big) || (fl == 0 && pool_in_smem)); };
     auto term_is_iso = [&](int t) { const int fl = flavour_of(t); return iso && (fl == 3 || (fl == 2 && iso_big)); };
-    const int64_t bcap_max = std::max(1, envi("EVR_SG4_BCAP", v2_on ? 3700 : 2350));                   // doubles per psi/acc buffer
+    const int64_t bcap_max = std::max(1, envi("EVR_SG4_BCAP", v2_on ? 3700 : 2800));                   // doubles per psi/acc buffer
     const int64_t target_items = (int64_t)p->sm_count * std::max(1, envi("EVR_SG4_ITEMS_PER_SM", 16));
     const int64_t bcap = std::max<int64_t>(1, std::min<int64_t>(bcap_max, (p->NQ_local * nb0 + target_items - 1) / target_items));
     struct Batch { std::vector<int> terms; int flavour, szclass; int64_t size; double cost; };
@@ -732,7 +732,7 @@ static int build_fast_path(evr_sg4_plan *p, int nb_Term, const int32_t *term_mod
     if (v2_on && (evr::v2_iso_set_attributes() || evr::v2_pool_set_attributes())) return 1;
     p->n_classes = 0;
     {
-        const int class_gsize[4] = {envi("EVR_SG4_G0", 256), envi("EVR_SG4_G1", 128), envi("EVR_SG4_G2", 64), envi("EVR_SG4_G3", 32)};
+        const int class_gsize[4] = {envi("EVR_SG4_G0", 256), envi("EVR_SG4_G1", 96), envi("EVR_SG4_G2", 64), envi("EVR_SG4_G3", 32)};
         int w0 = 0;
         while (w0 < n_items) {
             const int szc = batches[w0].szclass, fl = batches[w0].flavour;
@@ -776,6 +776,7 @@ static int build_fast_path(evr_sg4_plan *p, int nb_Term, const int32_t *term_mod
             }
             evr::FastClassDev &C = p->fclass[p->n_classes];
             C.term_begin = w0; C.n_terms = n; C.gsize = gsize; C.rt = rt ? 1 : 0; C.tri = tri ? 1 : 0; C.cap = (int)cap; C.cta_threads = ngrp * gsize;
+            C.counter = nullptr;
             p->fclass_smem[p->n_classes] = smem; p->fclass_ctas[p->n_classes] = ctas;
             p->fclass_flavour[p->n_classes] = iso_class ? (tri ? 2 : 3) : (rt ? 1 : (tri ? 2 : 0));
             p->fclass_is_iso[p->n_classes] = iso_class;
@@ -785,6 +786,10 @@ static int build_fast_path(evr_sg4_plan *p, int nb_Term, const int32_t *term_mod
         }
     }
     p->n_fitems = n_items;
+    if (!p->d_fcounters && cudaMalloc((void **)&p->d_fcounters, EVR_MAX_FCLASSES * sizeof(int)) != cudaSuccess)
+        return fail("evr_sg4: cudaMalloc(work counters) failed");
+    if (envi("EVR_SG4_DYNAMIC", 0) != 0)     // measured: 0.364 ms dynamic vs 0.355 static at L=7 (profiles/r2/sweep19_dynamic_items.txt): opt-in
+        for (int c = 0; c < p->n_classes; ++c) if (!p->fclass_v2[c]) p->fclass[c].counter = p->d_fcounters + c;
     cudaFree(p->d_fterms); cudaFree(p->d_fmap); cudaFree(p->d_fmats); cudaFree(p->d_fV);
     p->d_fterms = nullptr; p->d_fmap = nullptr; p->d_fmats = nullptr; p->d_fV = nullptr;
     if (upload(&p->d_fterms, fterms.data(), fterms.size())) return 1;
@@ -1046,6 +1051,7 @@ static int launch_direct(evr_sg4_plan *p, int npsi, const double *d_psi_user, do
             for (int c = 0; c < p->n_classes; ++c) if (p->fclass_is_iso[c]) (p->fclass_v2[c] ? any_v2_iso : any_v1_iso) = true;
             if (any_v1_iso && evr::iso_bind(p->device, p->iso_id, p->iso_blocks.data(), st)) return 1;
             if (any_v2_iso && evr::v2_iso_bind(p->device, p->iso_id, p->iso_blocks.data(), st)) return 1;
+            if (p->d_fcounters) CUDA_TRY(cudaMemsetAsync(p->d_fcounters, 0, EVR_MAX_FCLASSES * sizeof(int), st));
             const bool multi = p->n_classes > 1 && p->ev_fork != nullptr;
             if (multi) CUDA_TRY(cudaEventRecord(p->ev_fork, st));
             for (int c = 0; c < p->n_classes; ++c) {
@@ -1321,7 +1327,7 @@ extern "C" int evr_sg4_plan_destroy(evr_sg4_plan **pp)
     cudaFree(p->d_fterms); cudaFree(p->d_fmap); cudaFree(p->d_fmats); cudaFree(p->d_fV);
     cudaFree(p->d_fpos); cudaFree(p->d_gmap); cudaFree(p->d_perm); cudaFree(p->d_psi_int); cudaFree(p->d_Hpsi_int);
     cudaFree(p->d_GG); cudaFree(p->d_Jac); cudaFree(p->d_sq);
-    cudaFree(p->d_det_off); cudaFree(p->d_det_ent); cudaFree(p->d_stage);
+    cudaFree(p->d_det_off); cudaFree(p->d_det_ent); cudaFree(p->d_stage); cudaFree(p->d_fcounters);
     if (p->stream) cudaStreamDestroy(p->stream);
     for (int c = 0; c < EVR_MAX_FCLASSES; ++c) { if (p->side[c]) cudaStreamDestroy(p->side[c]); if (p->ev_join[c]) cudaEventDestroy(p->ev_join[c]); }
     if (p->ev_fork) cudaEventDestroy(p->ev_fork);

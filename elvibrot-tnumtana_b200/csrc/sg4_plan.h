@@ -83,6 +83,7 @@ struct evr_sg4_plan {
     int gclass_threads[4] = {0}, gclass_occ[4] = {0};
     size_t gclass_smem[4] = {0};
     evr::PlanDev pd{};
+    int *d_fcounters = nullptr;              // one work counter per fast-path launch (dynamic item scheduling)
     // deterministic mode (EVR_SG4_DETERMINISTIC=1 when the plan is created): staged scatter + ordered collection
     bool deterministic = false;
     long long *d_det_off = nullptr;          // [nb+1] entry-list offsets per packed element (internal order on the fast path)

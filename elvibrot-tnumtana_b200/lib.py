@@ -11,7 +11,7 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "libevr_sg4.so")
+SO_PATH = os.environ.get("EVR_SG4_LIB") or os.path.join(_HERE, "libevr_sg4.so")   # EVR_SG4_LIB: experiment builds
 _lib = None
 
 # enum values of include/evr_sg4.h

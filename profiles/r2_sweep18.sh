@@ -1,0 +1,17 @@
+#!/bin/bash
+cd "$GRAFT_REPO_ROOT" || exit 1
+O=gpurun_out
+mkdir -p $O
+: > $O/r2s18.txt
+run() { echo "## $*" >> $O/r2s18.txt; env "$@" timeout 300 python bench.py --no-cpu --no-e2e --steps 10 --warmup 3 2>>$O/r2s18_err.log | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['ms_per_step'], d['roofline']['frac'], d['roofline']['kernel_ms'])" >> $O/r2s18.txt 2>&1; }
+run EVR_SG4_BCAP=2800 EVR_SG4_G1=64
+run EVR_SG4_BCAP=2800 EVR_SG4_G1=32
+run EVR_SG4_BCAP=2800 EVR_SG4_G1=96
+run EVR_SG4_BCAP=2200 EVR_SG4_G1=64
+run EVR_SG4_BCAP=1800 EVR_SG4_G1=64
+run EVR_SG4_BCAP=1800 EVR_SG4_G1=32
+run EVR_SG4_BCAP=1400 EVR_SG4_G2=32
+run EVR_SG4_BCAP=3000 EVR_SG4_G1=64
+run EVR_SG4_BCAP=3500 EVR_SG4_G0=64
+run EVR_SG4_BCAP=4700 EVR_SG4_G0=128
+cat $O/r2s18.txt; tail -3 $O/r2s18_err.log
