@@ -620,7 +620,7 @@ static int build_fast_path(evr_sg4_plan *p, int nb_Term, const int32_t *term_mod
     const int64_t bcap_max = std::max(1, envi("EVR_SG4_BCAP", v2_on ? 3700 : 2800));                   // doubles per psi/acc buffer
     const int64_t target_items = (int64_t)p->sm_count * std::max(1, envi("EVR_SG4_ITEMS_PER_SM", 16));
     const int64_t bcap = std::max<int64_t>(1, std::min<int64_t>(bcap_max, (p->NQ_local * nb0 + target_items - 1) / target_items));
-    struct Batch { std::vector<int> terms; int flavour, szclass; int64_t size; double cost; };
+    struct Batch { std::vector<int> terms; int flavour, szclass; int64_t size; double cost, frac; };
     std::vector<Batch> batches;
     const int64_t th0 = envi("EVR_SG4_TH0", 3000), th1 = envi("EVR_SG4_TH1", 1400), th2 = envi("EVR_SG4_TH2", 600);
     {
@@ -654,15 +654,27 @@ static int build_fast_path(evr_sg4_plan *p, int nb_Term, const int32_t *term_mod
                 Bt.size = tsz * (hi - lo);
                 Bt.szclass = Bt.size > th0 ? 0 : (Bt.size > th1 ? 1 : (Bt.size > th2 ? 2 : 3));
                 Bt.cost = 0.0;
+                Bt.frac = ((double)b + 0.5) / (double)nbat;
                 for (int64_t j = lo; j < hi; ++j) Bt.cost += p->h_cost[tl[j]];
                 batches.push_back(std::move(Bt));
             }
         }
     }
-    // work order: size class (largest items first), then flavour, then cost descending
-    std::stable_sort(batches.begin(), batches.end(), [](const Batch &a, const Batch &b) {
+    // Work order: size class (largest items first), then flavour, then R rounds; round r holds the r-th R-th of the
+    // batches of EVERY shape, cost-descending inside the round.  Why rounds: the Smolyak weights alternate in sign with
+    // |l| and reach +-C(D-1, k) (462 at D = 12).  Summed shape by shape (plain cost order), the running value of a low
+    // packed element climbs to ~1e5 times its final value before the next shape cancels it, and the rounding of those
+    // partial sums is what separates two summation orders: 3e-13 ... 7e-13 relative L2 against the oracle at HH-12D L=7,
+    // with 5e-13 run-to-run (FP64 atomics), against a 1e-12 gate.  With all shapes advancing together the running sums stay
+    // near (fraction done) x (final value): 1e-13 with a fully interleaved order -- which costs 10 % (0.391 vs 0.356 ms: the
+    // cost order is what balances the static round-robin) -- so the compromise is R = 8 rounds (EVR_SG4_ORDER_ROUNDS;
+    // 1 = plain cost order).  Measurements: profiles/r2/parity_spread.txt.
+    const int rounds = std::max(1, envi("EVR_SG4_ORDER_ROUNDS", 8));
+    std::stable_sort(batches.begin(), batches.end(), [rounds](const Batch &a, const Batch &b) {
         if (a.szclass != b.szclass) return a.szclass < b.szclass;
         if (a.flavour != b.flavour) return a.flavour > b.flavour;
+        const int ra = (int)(a.frac * rounds), rb = (int)(b.frac * rounds);
+        if (ra != rb) return ra < rb;
         return a.cost > b.cost;
     });
     const int n_items = (int)batches.size();
