@@ -68,6 +68,7 @@ struct PlanDev {
     // deterministic mode: see FastPlanDev (entry = position in the plan's mapping slice)
     double *stage;
     long long stage_ld;
+    int use_dmma;                // FP64 tensor-core mode products for the large modes (EVR_SG4_DMMA=0 disables)
 };
 
 // ---- division by a per-term constant: q / d = umulhi(q, magic(d)) --------------------------------
@@ -94,6 +95,80 @@ __device__ __forceinline__ void mode_product(const double *__restrict__ M, int n
         for (int b = 0; b < n_in; ++b) s = fma(__ldg(M + q + n_out * b), x[left * b], s);
         out[o] = s;
     }
+}
+
+// ---- the same mode product on the FP64 tensor cores (DMMA, mma.sync.aligned.m8n8k4.f64) --------------------------
+// Used for modes whose matrices are large enough to be compute-bound (n_out, n_in >= EVR_DMMA_MIN: the Pl0 mode of
+// HCN_UT, 20 ... 80 points): one fragment load feeds 256 multiply-adds, where the thread-per-output product above issues
+// one matrix load and one shared-memory load per multiply-add.  Measured on the 80 x 80 matrix in isolation
+// (profiles/micro/dmma_vs_dfma.cu, profiles/r2/dmma_vs_dfma_pl0_mode.txt): 10.9 TFLOP/s against 4.7 (this file's scalar
+// product) and 5.6 (register tiles), 30 M tensor-pipe instructions instead of 242 M FP64-pipe instructions.  For the
+// 3 x 3 ... 15 x 15 matrices of every other mode an 8 x 8 x 4 fragment would be 14-47 % full: they stay on DFMA.
+// A warp owns 8 columns (a, c) and all row tiles of the output (<= EVR_DMMA_MAXROWT x 8 rows); edges are zero-padded.
+// Fragment layout (PTX ISA, m8n8k4 .f64): lane l holds A(row l/4, k l%4), B(k l%4, col l/4), C(row l/4, cols 2*(l%4)+{0,1}).
+#define EVR_DMMA_MIN 16
+#define EVR_DMMA_MAXROWT 32
+#define EVR_DMMA_ROWCHUNK 5
+__device__ __forceinline__ void dmma_m8n8k4(double &c0, double &c1, const double a, const double b)
+{
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+__device__ __forceinline__ void mode_product_dmma(const double *__restrict__ M, const int n_out, const int n_in,
+                                                  const double *in, double *out, const int left, const int right,
+                                                  const unsigned mg_left)
+{
+    const int warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5, lane = threadIdx.x & 31;
+    const int ar = lane >> 2, ak = lane & 3;
+    const int ncols = left * right, ncolt = (ncols + 7) >> 3, nrowt = (n_out + 7) >> 3;
+    for (int ct = warp; ct < ncolt; ct += nwarps) {
+        // B operand: column ct*8 + ar  ->  (a, c), base address of its pencil
+        const int colB = ct * 8 + ar;
+        const bool okB = colB < ncols;
+        const int cB = okB ? mdiv(colB, mg_left) : 0, aB = colB - cB * left;
+        const double *xB = in + aB + left * n_in * cB;
+        // row tiles in chunks of EVR_DMMA_ROWCHUNK (10 accumulator registers pairs per lane: the generic kernel is compiled for
+        // 64 registers); every chunk re-reads the B fragments of its columns from shared memory
+        for (int t0 = 0; t0 < nrowt; t0 += EVR_DMMA_ROWCHUNK) {
+            double acc[EVR_DMMA_ROWCHUNK][2];
+#pragma unroll
+            for (int t = 0; t < EVR_DMMA_ROWCHUNK; ++t) acc[t][0] = acc[t][1] = 0.0;
+            for (int k0 = 0; k0 < n_in; k0 += 4) {
+                const int k = k0 + ak;
+                const double bf = (okB && k < n_in) ? xB[left * k] : 0.0;
+#pragma unroll
+                for (int t = 0; t < EVR_DMMA_ROWCHUNK; ++t)
+                    if (t0 + t < nrowt) {
+                        const int row = (t0 + t) * 8 + ar;
+                        const double af = (row < n_out && k < n_in) ? __ldg(M + row + n_out * k) : 0.0;
+                        dmma_m8n8k4(acc[t][0], acc[t][1], af, bf);
+                    }
+            }
+            // C: rows (t0+t)*8 + ar, columns ct*8 + 2*ak + {0, 1}
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const int col = ct * 8 + 2 * ak + u;
+                if (col < ncols) {
+                    const int c = mdiv(col, mg_left), a = col - c * left;
+                    double *y = out + a + left * n_out * c;
+#pragma unroll
+                    for (int t = 0; t < EVR_DMMA_ROWCHUNK; ++t) {
+                        const int row = (t0 + t) * 8 + ar;
+                        if (t0 + t < nrowt && row < n_out) y[left * row] = acc[t][u];
+                    }
+                }
+            }
+        }
+    }
+}
+// dispatcher: DMMA for the large modes (whole warps only), DFMA otherwise
+__device__ __forceinline__ void mode_product_any(const double *__restrict__ M, int n_out, int n_in,
+                                                 const double *in, double *out, int left, int right,
+                                                 const unsigned mg_left, const unsigned mg_lo, const int use_dmma)
+{
+    if (use_dmma && n_out >= EVR_DMMA_MIN && n_in >= EVR_DMMA_MIN && n_out <= 8 * EVR_DMMA_MAXROWT && (blockDim.x & 31) == 0)
+        mode_product_dmma(M, n_out, n_in, in, out, left, right, mg_left);
+    else
+        mode_product(M, n_out, n_in, in, out, left, right, mg_left, mg_lo);
 }
 
 // ---- generic term kernel (any type_Op 0/1 term list, any mode sizes that fit) ----------
@@ -190,7 +265,7 @@ sg4_term_kernel_generic(const PlanDev P, const GenClassDev Cc, const int npsi,
                     const int nbk = s_tnb[k], nqk = s_tnq[k];
                     right /= nbk;
                     if (nbk == 1 && nqk == 1) continue;        // scalar folded into T.wfold by the plan
-                    mode_product(P.B + s_oB[k], nqk, nbk, cur, oth, left, right, s_mgq[k], s_mgq[k + 1]);
+                    mode_product_any(P.B + s_oB[k], nqk, nbk, cur, oth, left, right, s_mgq[k], s_mgq[k + 1], P.use_dmma);
                     double *t = cur; cur = oth; oth = t;
                     left *= nqk;
                     __syncthreads();
@@ -321,7 +396,7 @@ sg4_term_kernel_generic(const PlanDev P, const GenClassDev Cc, const int npsi,
                     const int nbk = s_tnb[k], nqk = s_tnq[k];
                     right /= nqk;
                     if (nbk == 1 && nqk == 1) continue;
-                    mode_product(P.BTw + s_oB[k], nbk, nqk, cur, oth, left, right, s_mgb[k], s_mgb[k + 1]);
+                    mode_product_any(P.BTw + s_oB[k], nbk, nqk, cur, oth, left, right, s_mgb[k], s_mgb[k + 1], P.use_dmma);
                     double *t = cur; cur = oth; oth = t;
                     left *= nbk;
                     __syncthreads();

@@ -86,7 +86,7 @@ sg4_nested_kernel(const PlanDev P, const int mode, const int nvec, const double 
                 const int nbk = s_tnb[k], nqk = s_tnq[k];
                 right /= nbk;
                 if (nbk == 1 && nqk == 1) { fold *= __ldg(P.B + s_oB[k]); continue; }
-                mode_product(P.B + s_oB[k], nqk, nbk, cur, oth, left, right, s_mgq[k], s_mgq[k + 1]);
+                mode_product_any(P.B + s_oB[k], nqk, nbk, cur, oth, left, right, s_mgq[k], s_mgq[k + 1], P.use_dmma);
                 double *t = cur; cur = oth; oth = t;
                 left *= nqk;
                 __syncthreads();
@@ -112,7 +112,7 @@ sg4_nested_kernel(const PlanDev P, const int mode, const int nvec, const double 
                 const int nbk = s_tnb[k], nqk = s_tnq[k];
                 right /= nqk;
                 if (nbk == 1 && nqk == 1) { fold *= __ldg(P.BTw + s_oB[k]); continue; }
-                mode_product(P.BTw + s_oB[k], nbk, nqk, cur, oth, left, right, s_mgb[k], s_mgb[k + 1]);
+                mode_product_any(P.BTw + s_oB[k], nbk, nqk, cur, oth, left, right, s_mgb[k], s_mgb[k + 1], P.use_dmma);
                 double *t = cur; cur = oth; oth = t;
                 left *= nbk;
                 __syncthreads();
@@ -138,7 +138,7 @@ sg4_nested_kernel(const PlanDev P, const int mode, const int nvec, const double 
                 else { k = pass ? der2 : der1; if (k < 0) continue; M = P.D1 + s_oG[k]; }
                 const int n = s_tnq[k];
                 int left = s_str[k], right = (nq / (left * n)) * nb0;
-                mode_product(M, n, n, cur, oth, left, right, s_mgq[k], s_mgq[k + 1]);
+                mode_product_any(M, n, n, cur, oth, left, right, s_mgq[k], s_mgq[k + 1], P.use_dmma);
                 double *t = cur; cur = oth; oth = t;
                 __syncthreads();
             }

@@ -304,6 +304,10 @@ int evr::plan_create_single(evr_sg4_plan **out, int device,
     pd.cap = p->cap; pd.terms = p->d_terms; pd.lev = p->d_lev; pd.map = p->d_map;
     pd.nq_of = p->d_nq_of; pd.nb_of = p->d_nb_of; pd.offB = p->d_offB; pd.offG = p->d_offG;
     pd.B = p->d_B; pd.BTw = p->d_BTw; pd.D1 = p->d_D1; pd.D2 = p->d_D2;
+    // DMMA mode products (sg4_kernels.cuh: mode_product_dmma) are opt-in: 2.3 x faster on the 80 x 80 mode in isolation, but
+    // the HCN_UT terms offer only ~170 columns per matrix and the call is latency-bound: 122 vs 86 us per H|psi>, 228 vs 208 us
+    // for a 27-vector block (profiles/r2/dmma_in_generic_kernel.txt)
+    pd.use_dmma = (getenv("EVR_SG4_DMMA") && atoi(getenv("EVR_SG4_DMMA")) != 0) ? 1 : 0;
     *out = p;
     return 0;
 }
