@@ -6,6 +6,7 @@
 // that uses it: no matrix loads, no matrix registers.  The freed registers pay for larger tiles (3x3x3, 5x5, 3x5, 3x7,
 // 3x9 values per thread, 128 registers at <= 512 threads per CTA) and therefore fewer shared-memory sweeps per term.
 #include <cuda_runtime.h>
+#include <mutex>
 #include "sg4_fast.cuh"
 
 namespace evr {
@@ -21,6 +22,8 @@ int iso_set_attributes()
 int iso_bind(int device, int id, const double *blocks, cudaStream_t st)
 {
     static int bound_id[64] = {0};
+    static std::mutex mtx;                      // plans of several host threads (multi-device layer) bind concurrently
+    std::lock_guard<std::mutex> lock(mtx);
     int &cur = bound_id[device & 63];
     if (cur == id) return 0;
     // another plan's matrices (or none) are loaded: replace them.  Rare (alternating plans with different bases on one
@@ -28,6 +31,8 @@ int iso_bind(int device, int id, const double *blocks, cudaStream_t st)
     if (cur != 0 && cudaDeviceSynchronize() != cudaSuccess) return fail("evr_sg4: cudaDeviceSynchronize failed");
     if (cudaMemcpyToSymbolAsync(c_iso, blocks, sizeof(double) * EVR_ISO_LEN, 0, cudaMemcpyHostToDevice, st) != cudaSuccess)
         return fail("evr_sg4: cudaMemcpyToSymbolAsync(c_iso) failed");
+    // the array must be populated before a launch of this plan on ANY stream may find it "bound"
+    if (cudaStreamSynchronize(st) != cudaSuccess) return fail("evr_sg4: cudaStreamSynchronize failed");
     cur = id;
     return 0;
 }

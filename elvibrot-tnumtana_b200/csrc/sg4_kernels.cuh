@@ -483,6 +483,8 @@ sg4_term_kernel_type10(const PlanDev P, const Op10Dev O, const int npsi,
     int *s_oB    = s_tnb + P.D;
     int *s_oG    = s_oB + P.D;
     int *s_str   = s_oG + P.D;
+    unsigned *s_mgs = reinterpret_cast<unsigned *>(s_str + P.D);   // magic of the grid stride of mode k
+    unsigned *s_mgn = s_mgs + P.D;                                 // magic of nq_k
 
     for (int i = threadIdx.x; i < nT; i += blockDim.x) {
         s_nq_of[i] = P.nq_of[i]; s_nb_of[i] = P.nb_of[i];
@@ -505,7 +507,8 @@ sg4_term_kernel_type10(const PlanDev P, const Op10Dev O, const int npsi,
                 const int i = k * (P.LG + 1) + lev[k];
                 s_tnq[k] = s_nq_of[i]; s_tnb[k] = s_nb_of[i];
                 s_oB[k] = s_offB[i];   s_oG[k] = s_offG[i];
-                s_str[k] = str; str *= s_nq_of[i];
+                s_str[k] = str; s_mgs[k] = magic_of(str); s_mgn[k] = magic_of(s_nq_of[i]);
+                str *= s_nq_of[i];
             }
         }
         __syncthreads();
@@ -543,7 +546,8 @@ sg4_term_kernel_type10(const PlanDev P, const Op10Dev O, const int npsi,
             const int k = O.act_mode[a];
             const double *M = P.D1 + s_oG[k];
             const int nk = s_tnq[k], st = s_str[k];
-            const int qk = (q / st) % nk;
+            const int qd = mdiv(q, s_mgs[k]);                        // no integer division per point
+            const int qk = qd - mdiv(qd, s_mgn[k]) * nk;
             const int base = q - qk * st;
             double s = 0.0;
             for (int b = 0; b < nk; ++b) s = fma(__ldg(M + qk + nk * b), arr[base + b * st], s);
@@ -556,9 +560,9 @@ sg4_term_kernel_type10(const PlanDev P, const Op10Dev O, const int npsi,
             for (int a = 0; a < n; ++a)
                 for (int q = threadIdx.x; q < nq; q += blockDim.x) sR[(size_t)a * O.nqmax + q] = deriv(chi, a, q);
             __syncthreads();
-            double acc[EVR_OP10_PTS];
-#pragma unroll
-            for (int u = 0; u < EVR_OP10_PTS; ++u) acc[u] = 0.0;
+            // sum_i d_i [Jac sum_j G^{ji} d_j phi] accumulates in the second buffer (every thread owns its points), so the term
+            // size is bounded by shared memory only
+            for (int q = threadIdx.x; q < nq; q += blockDim.x) oth[c * nq + q] = 0.0;
             for (int i = 0; i < n; ++i) {
                 for (int q = threadIdx.x; q < nq; q += blockDim.x) {
                     double s = 0.0;
@@ -567,18 +571,12 @@ sg4_term_kernel_type10(const PlanDev P, const Op10Dev O, const int npsi,
                     chi[q] = s * __ldg(Jq + q);
                 }
                 __syncthreads();
-#pragma unroll
-                for (int u = 0; u < EVR_OP10_PTS; ++u) {
-                    const int q = threadIdx.x + u * blockDim.x;
-                    if (q < nq) acc[u] += deriv(chi, i, q);
-                }
+                for (int q = threadIdx.x; q < nq; q += blockDim.x) oth[c * nq + q] += deriv(chi, i, q);
                 __syncthreads();
             }
-#pragma unroll
-            for (int u = 0; u < EVR_OP10_PTS; ++u) {
-                const int q = threadIdx.x + u * blockDim.x;
-                if (q < nq) {
-                    double r = -0.5 * acc[u] / (__ldg(Jq + q) * __ldg(Sq + q));
+            {
+                for (int q = threadIdx.x; q < nq; q += blockDim.x) {
+                    double r = -0.5 * oth[c * nq + q] / (__ldg(Jq + q) * __ldg(Sq + q));
                     if (O.has_V)
                         for (int j = 0; j < nb0; ++j)
                             r = fma(__ldg(O.V + (long long)(c + nb0 * j) * P.NQ_local + T.grid_off + q), cur[j * nq + q], r);

@@ -825,6 +825,11 @@ static int build_fast_path(evr_sg4_plan *p, int nb_Term, const int32_t *term_mod
     p->iso_blocks.swap(iso_blocks);
     { static int next_id = 0; p->iso_id = ++next_id; }
     f.dbg = getenv("EVR_SG4_DEBUG") ? atoi(getenv("EVR_SG4_DEBUG")) : 0;
+    if (f.dbg & (4 | 8 | 16 | 32)) {            // phase-isolation switches of the measurements in profiles/: results are WRONG
+        static bool warned = false;
+        if (!warned) fprintf(stderr, "evr_sg4: EVR_SG4_DEBUG=%d disables parts of the H|psi> action (timing experiments only)\n", f.dbg);
+        warned = true;
+    }
     // the L2 prefetch of the next term's slices stopped paying once the slices stream through LDGSTS (measured: equal
     // times); off unless EVR_SG4_PREFETCH=1
     if (!getenv("EVR_SG4_PREFETCH") || atoi(getenv("EVR_SG4_PREFETCH")) == 0) f.dbg |= 64;
@@ -971,10 +976,9 @@ extern "C" int evr_sg4_plan_set_op10(evr_sg4_plan *p, int n_act, const int32_t *
     }
     int nqmax = 1;
     for (int t = 0; t < p->n_terms; ++t) nqmax = std::max(nqmax, (int)p->h_tab_nq[p->iG_begin + t]);
-    if (nqmax > EVR_OP10_PTS * 256) return fail("evr_sg4_plan_set_op10: a Smolyak term has more than 2048 grid points (not supported for type_Op=10)");
     O.nqmax = nqmax;
     const int nT = p->D * (p->LG + 1);
-    p->smem10 = ((size_t)2 * p->cap + (size_t)(n_act + 1) * nqmax) * sizeof(double) + (size_t)(4 * nT + 5 * p->D) * sizeof(int);
+    p->smem10 = ((size_t)2 * p->cap + (size_t)(n_act + 1) * nqmax) * sizeof(double) + (size_t)(4 * nT + 7 * p->D) * sizeof(int);
     if (p->smem10 > 227 * 1024) return fail("evr_sg4_plan_set_op10: shared-memory budget exceeded for this n_act / term size");
     const size_t blk = (size_t)std::max<int64_t>(p->NQ_local, 1);
     auto up_slice = [&](double **d, const double *h, int ncomp) -> int {

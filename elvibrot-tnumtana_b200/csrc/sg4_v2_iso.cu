@@ -2,6 +2,7 @@
 // Own translation unit (parallel build); it therefore owns its copy of the __constant__ matrix array, bound per plan
 // like the one of sg4_iso.cu.
 #include <cuda_runtime.h>
+#include <mutex>
 #include "sg4_fast2.cuh"
 
 namespace evr {
@@ -17,6 +18,8 @@ int v2_iso_set_attributes()
 int v2_iso_bind(int device, int id, const double *blocks, cudaStream_t st)
 {
     static int bound_id[64] = {0};
+    static std::mutex mtx;
+    std::lock_guard<std::mutex> lock(mtx);
     int &cur = bound_id[device & 63];
     if (cur == id) return 0;
     // another plan's matrices (or none) are loaded: replace them.  Rare (alternating plans with different bases on one

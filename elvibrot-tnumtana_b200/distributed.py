@@ -61,21 +61,38 @@ class TermParallelOp:
         import torch.distributed as dist
         dev = torch.device("cuda", torch.cuda.current_device())
         ok, t, hdl = 0, None, None
-        if self.world > 1 and os.environ.get("EVR_SG4_ALLREDUCE", "p2p") != "nccl" and self.world <= 16:
+        want = self.world > 1 and os.environ.get("EVR_SG4_ALLREDUCE", "p2p") != "nccl" and self.world <= 16
+
+        def agree(flag: int) -> int:        # MIN over the ranks: everybody takes the same branch
+            if self.world == 1:
+                return flag
+            f = torch.tensor([flag], dtype=torch.int32, device=dev)
+            dist.all_reduce(f, op=dist.ReduceOp.MIN, group=self.group)
+            return int(f.item())
+
+        # step 1 (local, cannot hang): import + allocation; agreed on BEFORE the collective rendezvous, so that a rank
+        # that fails here does not leave the others waiting inside it
+        symm_mem = None
+        if want:
             try:
                 import torch.distributed._symmetric_memory as symm_mem
-                grp = self.group if self.group is not None else dist.group.WORLD
                 t = symm_mem.empty(*shape, dtype=torch.float64, device=dev)
-                hdl = symm_mem.rendezvous(t, grp)
-                ok = 1 if (hdl.world_size == self.world and hdl.rank == self.rank and t.data_ptr() % 16 == 0
-                            and int(hdl.buffer_ptrs[self.rank]) == t.data_ptr()) else 0
+                ok = 1
             except Exception as e:      # noqa: BLE001 - any failure means "use NCCL", agreed on by all ranks below
                 self._symm_error = repr(e)
                 ok = 0
-        if self.world > 1:
-            flag = torch.tensor([ok], dtype=torch.int32, device=dev)
-            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
-            ok = int(flag.item())
+        ok = agree(ok) if self.world > 1 else 0
+        # step 2 (collective): rendezvous, then agree on its outcome
+        if ok:
+            try:
+                grp = self.group if self.group is not None else dist.group.WORLD
+                hdl = symm_mem.rendezvous(t, grp)
+                ok = 1 if (hdl.world_size == self.world and hdl.rank == self.rank and t.data_ptr() % 16 == 0
+                           and int(hdl.buffer_ptrs[self.rank]) == t.data_ptr()) else 0
+            except Exception as e:      # noqa: BLE001
+                self._symm_error = repr(e)
+                ok = 0
+            ok = agree(ok)
         if not ok:
             return torch.empty(*shape, dtype=torch.float64, device=dev)
         ptrs = (C.c_void_p * self.world)(*[int(p) for p in hdl.buffer_ptrs])

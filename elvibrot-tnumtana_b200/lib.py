@@ -54,7 +54,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
 
 def lib():
-    """Load the shared object (building it first if the sources are newer)."""
+    """Load the shared object; it is built first only when it is missing (``build()`` is the staleness-aware entry:
+    __graft_entry__.build() calls it; a GPU box gets the prebuilt library with the snapshot and must not rebuild)."""
     global _lib
     if _lib is not None:
         return _lib

@@ -1,7 +1,9 @@
 // Test driver of the C++ host mirror (elvibrot-tnumtana_b200/host/evr_oppsi.hpp).
 // Reads a problem dumped by tests/test_gpu_parity.py::test_cpp_host_mirror (flat little-endian arrays, the
 // exact arguments of evr_sg4_plan_create / evr_sg4_plan_set_op), applies H through sub_OpPsi / sub_TabOpPsi
-// and writes the results back.  usage: host_mirror_main <in.bin> <out.bin>
+// and writes the results back.  usage: host_mirror_main <in.bin> <out.bin> [ndev]
+// ndev > 1: evr_sg4_set_devices(ndev) first -- the same program then drives ndev GPUs (term ranges per device, NVLink
+// reduction, slice-wise host copies) through include/evr_sg4.h only.
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -38,7 +40,9 @@ int main(int argc, char **argv)
 
     evr::param_Op H;
     H.nb = nb; H.nb0 = nb0;
+    const int ndev = argc > 3 ? atoi(argv[3]) : 1;
     try {
+        if (ndev > 1) evr::check(evr_sg4_set_devices(ndev), "set_devices");
         evr::check(evr_sg4_plan_create(&H.plan, -1, D, nb_SG, nb0, nb, LG, tab_l.data(), W.data(), tnq.data(), tnb.data(), map.data(),
                                        nq_of.data(), nb_of.data(), B.data(), BTw.data(), D1.data(), D2.data(), 0, nb_SG), "plan_create");
         evr::check(evr_sg4_plan_set_op(H.plan, type_Op, nb_Term, term_mode.data(), gz.data(), gc.data(), mc.data(), gp.data()), "plan_set_op");
@@ -59,6 +63,7 @@ int main(int argc, char **argv)
         FILE *g = fopen(argv[2], "wb");
         long long cnt = stops; fwrite(&cnt, sizeof(cnt), 1, g);
         cnt = H.nb_OpPsi; fwrite(&cnt, sizeof(cnt), 1, g);
+        if (ndev > 1 && evr_sg4_plan_info(H.plan, EVR_INFO_DEVICES) != ndev) { fprintf(stderr, "plan does not span %d devices\n", ndev); return 4; }
         for (int i = 0; i < npsi; ++i) fwrite(TabH[i].RvecB.data(), sizeof(double), n, g);
         for (int i = 0; i < ncplx; ++i) fwrite(CH[i].CvecB.data(), sizeof(double), 2 * n, g);
         fclose(g);

@@ -187,6 +187,15 @@ def test_type_op_10_cached_metric(evr):
     nov = evr.workloads.synthetic_type10(evr.workloads.hm_sg4_basis(3, 3, 3, 1, 2), with_V=False)
     psi = random_psi(nov.BasisnD.nb, 1, 22)
     assert rel_l2(nov.apply_host(psi), oracle_apply10(nov, psi)) < TOL
+    # terms of more than 2048 grid points (round-1 limit of this kernel): 60 x 7 x 5 = 2100 at l = (2, 3, 2)
+    big = evr.workloads.hm_sg4_basis(3, 7, 7, [20, 1, 1], [20, 2, 2])
+    assert int(big.tab_nq_OF_SRep.max()) > 2048
+    op = evr.workloads.synthetic_type10(big)
+    psi = random_psi(big.nb, 2, 23)
+    ref = oracle_apply10(op, psi)
+    out = op.apply_host(psi)
+    for i in range(2):
+        assert rel_l2(out[i], ref[i]) < TOL
 
 
 def test_gpu_pyrazine_autocorrelation_matches_reference(evr, golden):
@@ -201,10 +210,16 @@ def test_gpu_pyrazine_autocorrelation_matches_reference(evr, golden):
     assert max(np.abs(c.real - rows[:, 1]).max(), np.abs(c.imag - rows[:, 2]).max(), np.abs(np.abs(c) - rows[:, 3]).max()) < 1e-10
 
 
-def test_cpp_host_mirror(evr, tmp_path):
+@pytest.mark.parametrize("ndev", [1, 2])
+def test_cpp_host_mirror(evr, tmp_path, ndev):
     """The C++ mirror of mod_OpPsi (host/evr_oppsi.hpp: param_psi, param_Op, sub_OpPsi, sub_TabOpPsi) driven by a
-    compiled program over the C-ABI: block of real vectors + complex wave packets, pyrazine two-state model."""
+    compiled program over the C-ABI: block of real vectors + complex wave packets, pyrazine two-state model.
+    ndev = 2: the same compiled program calls evr_sg4_set_devices(2) and drives two GPUs through include/evr_sg4.h only."""
     import os
+    if ndev > 1:
+        import torch
+        if torch.cuda.device_count() < ndev:
+            pytest.skip("needs two GPUs (gpurun --gpus 2)")
     import struct
     import subprocess
     from helpers import flat_op
@@ -236,7 +251,7 @@ def test_cpp_host_mirror(evr, tmp_path):
             f.write(blk(np.zeros(0) if g is None else g, np.float64))
         f.write(blk(psi, np.float64))
         f.write(blk(np.stack([cpsi.real, cpsi.imag], axis=-1), np.float64))
-    subprocess.check_call([str(exe), str(tmp_path / "in.bin"), str(tmp_path / "out.bin")])
+    subprocess.check_call([str(exe), str(tmp_path / "in.bin"), str(tmp_path / "out.bin")] + ([str(ndev)] if ndev > 1 else []))
     raw = open(tmp_path / "out.bin", "rb").read()
     stops, count = struct.unpack("<qq", raw[:16])
     assert stops == 2                       # both reference STOP conditions raised
