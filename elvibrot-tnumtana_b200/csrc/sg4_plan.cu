@@ -668,7 +668,7 @@ static int build_fast_path(evr_sg4_plan *p, int nb_Term, const int32_t *term_mod
     // batches of EVERY shape, cost-descending inside the round.  Why rounds: the Smolyak weights alternate in sign with
     // |l| and reach +-C(D-1, k) (462 at D = 12).  Summed shape by shape (plain cost order), the running value of a low
     // packed element climbs to ~1e5 times its final value before the next shape cancels it, and the rounding of those
-    // partial sums is what separates two summation orders: 3e-13 ... 7e-13 relative L2 against the oracle at HH-12D L=7,
+    // partial sums is what separates two summation orders: 3e-13 ... 7e-13 relative L2 against the CPU restatement of the reference at HH-12D L=7,
     // with 5e-13 run-to-run (FP64 atomics), against a 1e-12 gate.  With all shapes advancing together the running sums stay
     // near (fraction done) x (final value): 1e-13 with a fully interleaved order -- which costs 10 % (0.391 vs 0.356 ms: the
     // cost order is what balances the static round-robin) -- so the compromise is R = 8 rounds (EVR_SG4_ORDER_ROUNDS;
