@@ -934,22 +934,4 @@ sg4_term_kernel_fast(const FastPlanDev P, const FastClassDev Cc, const int npsi,
     }
 }
 
-// packed vectors between the caller's order (RvecB) and the internal block order
-static __global__ void sg4_permute_in(const int32_t *__restrict__ perm, const long long nb, const int nvecs,
-                               const double *__restrict__ src, double *__restrict__ dst)
-{
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nb; i += (long long)gridDim.x * blockDim.x) {
-        const int r = __ldg(perm + i);
-        for (int v = 0; v < nvecs; ++v) dst[v * nb + i] = __ldg(src + v * nb + r);
-    }
-}
-static __global__ void sg4_permute_out(const int32_t *__restrict__ perm, const long long nb, const int nvecs,
-                                const double *__restrict__ src, double *__restrict__ dst)
-{
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nb; i += (long long)gridDim.x * blockDim.x) {
-        const int r = __ldg(perm + i);
-        for (int v = 0; v < nvecs; ++v) dst[v * nb + r] = src[v * nb + i];
-    }
-}
-
 } // namespace evr

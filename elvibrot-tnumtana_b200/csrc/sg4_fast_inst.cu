@@ -1,38 +1,59 @@
-// sg4_fast_inst.cu -- instantiations and launchers of the separable-KEO term kernel (sg4_fast.cuh) whose 1-D
-// matrices are read from the shared-memory pool (any set of per-mode matrices); the variants that read the pool from
-// global memory live in sg4_fast_inst0.cu (separate translation unit: parallel build).
+// sg4_fast_inst.cu -- launch dispatch of the separable-KEO term kernel (sg4_fast.cuh) over its instantiations, which live
+// in one translation unit each (sg4_fast_k{1,0}{p,r,t}.cu: pool in shared / global memory x templated / runtime-size / cube
+// tiles), and the permutation kernels of the block-ordered packed vector.
 #include <cuda_runtime.h>
-#include "sg4_fast.cuh"
+#include "sg4_fast_types.h"
 
 namespace evr {
 
-#define EVR_FAST_VARIANTS(X) X(1, false, false) X(1, true, false) X(1, false, true)
+int fast_attr_1p();
+int fast_launch_1p(int, int, size_t, cudaStream_t, const FastPlanDev &, const FastClassDev &, int, const double *, double *);
+int fast_attr_1r();
+int fast_launch_1r(int, int, size_t, cudaStream_t, const FastPlanDev &, const FastClassDev &, int, const double *, double *);
+int fast_attr_1t();
+int fast_launch_1t(int, int, size_t, cudaStream_t, const FastPlanDev &, const FastClassDev &, int, const double *, double *);
+int fast_attr_0p();
+int fast_launch_0p(int, int, size_t, cudaStream_t, const FastPlanDev &, const FastClassDev &, int, const double *, double *);
+int fast_attr_0r();
+int fast_launch_0r(int, int, size_t, cudaStream_t, const FastPlanDev &, const FastClassDev &, int, const double *, double *);
+int fast_attr_0t();
+int fast_launch_0t(int, int, size_t, cudaStream_t, const FastPlanDev &, const FastClassDev &, int, const double *, double *);
 
-int fast0_set_attributes();
-int fast0_launch(bool rt, bool tri, int nctas, int nthr, size_t smem, cudaStream_t st,
-                 const FastPlanDev &P, const FastClassDev &C, int npsi, const double *psi, double *Hpsi);
+// packed vectors between the caller's order (RvecB) and the internal block order
+static __global__ void sg4_permute_in(const int32_t *__restrict__ perm, const long long nb, const int nvecs,
+                               const double *__restrict__ src, double *__restrict__ dst)
+{
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nb; i += (long long)gridDim.x * blockDim.x) {
+        const int r = __ldg(perm + i);
+        for (int v = 0; v < nvecs; ++v) dst[v * nb + i] = __ldg(src + v * nb + r);
+    }
+}
+static __global__ void sg4_permute_out(const int32_t *__restrict__ perm, const long long nb, const int nvecs,
+                                const double *__restrict__ src, double *__restrict__ dst)
+{
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nb; i += (long long)gridDim.x * blockDim.x) {
+        const int r = __ldg(perm + i);
+        for (int v = 0; v < nvecs; ++v) dst[v * nb + r] = src[v * nb + i];
+    }
+}
 
 int fast_set_attributes()
 {
-    if (fast0_set_attributes()) return 1;
-#define X(mm, rt, tri) \
-    if (cudaFuncSetAttribute(sg4_term_kernel_fast<mm, rt, tri>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) \
-        return fail("evr_sg4: cudaFuncSetAttribute(fast kernel) failed");
-    EVR_FAST_VARIANTS(X)
-#undef X
-    return 0;
+    return fast_attr_1p() || fast_attr_1r() || fast_attr_1t() || fast_attr_0p() || fast_attr_0r() || fast_attr_0t();
 }
 
 int fast_launch(int mm, bool rt, bool tri, int nctas, int nthr, size_t smem, cudaStream_t st,
                 const FastPlanDev &P, const FastClassDev &C, int npsi, const double *psi, double *Hpsi)
 {
     if (tri) rt = false;
-    if (mm == 0) return fast0_launch(rt, tri, nctas, nthr, smem, st, P, C, npsi, psi, Hpsi);
-#define X(m_, r_, t_) \
-    if (mm == m_ && rt == r_ && tri == t_) { sg4_term_kernel_fast<m_, r_, t_><<<nctas, nthr, smem, st>>>(P, C, npsi, psi, Hpsi); return 0; }
-    EVR_FAST_VARIANTS(X)
-#undef X
-    return fail("evr_sg4: no such fast-kernel variant");
+    if (mm) {
+        if (tri) return fast_launch_1t(nctas, nthr, smem, st, P, C, npsi, psi, Hpsi);
+        if (rt) return fast_launch_1r(nctas, nthr, smem, st, P, C, npsi, psi, Hpsi);
+        return fast_launch_1p(nctas, nthr, smem, st, P, C, npsi, psi, Hpsi);
+    }
+    if (tri) return fast_launch_0t(nctas, nthr, smem, st, P, C, npsi, psi, Hpsi);
+    if (rt) return fast_launch_0r(nctas, nthr, smem, st, P, C, npsi, psi, Hpsi);
+    return fast_launch_0p(nctas, nthr, smem, st, P, C, npsi, psi, Hpsi);
 }
 
 int fast_permute(bool in, const int32_t *perm, long long nb, int nvecs, const double *src, double *dst, cudaStream_t st)
