@@ -1163,7 +1163,8 @@ static int launch(evr_sg4_plan *p, int npsi, const double *d_psi_user, double *d
                   const ScaleArgs sc = ScaleArgs{false, 0.0, 1.0})
 {
     static const bool graphs_on = getenv("EVR_SG4_GRAPH") && atoi(getenv("EVR_SG4_GRAPH")) != 0;
-    if (!graphs_on || p->n_terms == 0 || p->stream == nullptr) return launch_direct(p, npsi, d_psi_user, d_Hpsi_user, st, sc);
+    // (the deterministic mode allocates its staging vector inside the launch sequence: not captured)
+    if (!graphs_on || p->deterministic || p->n_terms == 0 || p->stream == nullptr) return launch_direct(p, npsi, d_psi_user, d_Hpsi_user, st, sc);
     for (auto &g : p->graphs)
         if (g.npsi == npsi && g.psi == d_psi_user && g.Hpsi == d_Hpsi_user && g.scaled == sc.on && g.E0 == sc.E0 && g.Esc == sc.Esc) {
             if (bind_iso_arrays(p, st)) return 1;               // another plan may have re-bound the constant arrays

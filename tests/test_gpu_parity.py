@@ -440,7 +440,8 @@ def test_benchmarked_configuration_parity(evr, L):
     basis, op, psi, ref = _bench_case(evr, L)
     assert basis.nqq == {6: 4195284, 7: 23826372}[L]
     out = op.apply_host(psi)
-    assert op.info(evr.lib.INFO_PATH) == 1 and op.info(evr.lib.INFO_ISO) == 1
+    if not any(os.environ.get(k) for k in ("EVR_SG4_ISO", "EVR_SG4_FORCE_GENERIC")):      # default kernel selection
+        assert op.info(evr.lib.INFO_PATH) == 1 and op.info(evr.lib.INFO_ISO) == 1
     assert rel_l2(out[0], ref[0]) < TOL, rel_l2(out[0], ref[0])
 
 
