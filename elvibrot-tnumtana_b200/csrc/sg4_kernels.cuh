@@ -32,8 +32,11 @@ struct TermDev {                 // one per Smolyak term of this plan's range (w
 
 struct GenClassDev {             // one launch of the generic kernel: terms of similar size, one CTA size
     int term_begin, n_terms;     // range in work order
-    int cap;                     // doubles per shared-memory buffer (max term size of the class * nb0)
+    int cap;                     // doubles per work buffer (max term size of the class * nb0)
     int dcache;                  // 1: third buffer holds the first derivative of the current sweep mode
+    double *scratch;             // class of terms too large for shared memory: [CTAs][2 or 3][cap] in global memory, else nullptr
+    const int *list;             // nullptr: terms term_begin .. term_begin + n_terms of the work order; else work-order indices
+                                 // list[term_begin ..] (the terms a fast-path plan leaves to this kernel)
 };
 
 struct OpTermDev {               // one per live (not grid_zero) operator term
@@ -75,10 +78,35 @@ struct PlanDev {
 // magic(d) = floor(2^32 / d) + 1, exact while q * d < 2^32 (term sizes are < 2^15 values); d = 1 is encoded as 0
 __device__ __forceinline__ unsigned magic_of(const int d) { return d <= 1 ? 0u : 0xFFFFFFFFu / (unsigned)d + 1u; }
 __device__ __forceinline__ int mdiv(const int q, const unsigned mg) { return mg ? (int)__umulhi((unsigned)q, mg) : q; }
+// BIG = true (terms that do not fit in shared memory, work buffers in global memory): the per-term constant is the
+// divisor itself and the division is the hardware sequence -- no bound on q * d
+template <bool BIG> __device__ __forceinline__ unsigned magic_ofT(const int d) { return BIG ? (unsigned)(d <= 1 ? 0 : d) : magic_of(d); }
+template <bool BIG> __device__ __forceinline__ int mdivT(const int q, const unsigned mg)
+{
+    if (BIG) return mg ? (int)((unsigned)q / mg) : q;
+    return mdiv(q, mg);
+}
+
+// ---- sum_b M[b*ms] * x[b*xs] with four independent partial sums: a single accumulator makes every multiply-add wait for
+// the previous one (the products of the large modes, n = 20 ... 80, are chains of n dependent DFMAs per output)
+__device__ __forceinline__ double dot4(const double *__restrict__ M, const int ms, const double *x, const int xs, const int n)
+{
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    int b = 0;
+    for (; b + 3 < n; b += 4) {
+        s0 = fma(__ldg(M + (b + 0) * ms), x[(b + 0) * xs], s0);
+        s1 = fma(__ldg(M + (b + 1) * ms), x[(b + 1) * xs], s1);
+        s2 = fma(__ldg(M + (b + 2) * ms), x[(b + 2) * xs], s2);
+        s3 = fma(__ldg(M + (b + 3) * ms), x[(b + 3) * xs], s3);
+    }
+    for (; b < n; ++b) s0 = fma(__ldg(M + b * ms), x[b * xs], s0);
+    return n < 4 ? s0 : (s0 + s1) + (s2 + s3);
+}
 
 // ---- generic one-mode product through shared memory ----------------------------------
 //   out[a + left*(q + n_out*c)] = sum_b M[q + n_out*b] * in[a + left*(b + n_in*c)]
 //   a < left, c < right (right already includes the channel count), M in global (L1-resident).
+template <bool BIG = false>
 __device__ __forceinline__ void mode_product(const double *__restrict__ M, int n_out, int n_in,
                                              const double *in, double *out, int left, int right,
                                              const unsigned mg_left, const unsigned mg_lo)
@@ -86,14 +114,11 @@ __device__ __forceinline__ void mode_product(const double *__restrict__ M, int n
     const int total = left * n_out * right;
     const int lo = left * n_out;
     for (int o = threadIdx.x; o < total; o += blockDim.x) {
-        const int c = mdiv(o, mg_lo);
+        const int c = mdivT<BIG>(o, mg_lo);
         const int r = o - c * lo;
-        const int q = mdiv(r, mg_left);
+        const int q = mdivT<BIG>(r, mg_left);
         const int a = r - q * left;
-        const double *x = in + a + left * n_in * c;
-        double s = 0.0;
-        for (int b = 0; b < n_in; ++b) s = fma(__ldg(M + q + n_out * b), x[left * b], s);
-        out[o] = s;
+        out[o] = dot4(M + q, n_out, in + a + left * n_in * c, left, n_in);
     }
 }
 
@@ -113,6 +138,7 @@ __device__ __forceinline__ void dmma_m8n8k4(double &c0, double &c1, const double
 {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
+template <bool BIG = false>
 __device__ __forceinline__ void mode_product_dmma(const double *__restrict__ M, const int n_out, const int n_in,
                                                   const double *in, double *out, const int left, const int right,
                                                   const unsigned mg_left)
@@ -124,7 +150,7 @@ __device__ __forceinline__ void mode_product_dmma(const double *__restrict__ M, 
         // B operand: column ct*8 + ar  ->  (a, c), base address of its pencil
         const int colB = ct * 8 + ar;
         const bool okB = colB < ncols;
-        const int cB = okB ? mdiv(colB, mg_left) : 0, aB = colB - cB * left;
+        const int cB = okB ? mdivT<BIG>(colB, mg_left) : 0, aB = colB - cB * left;
         const double *xB = in + aB + left * n_in * cB;
         // row tiles in chunks of EVR_DMMA_ROWCHUNK (10 accumulator registers pairs per lane: the generic kernel is compiled for
         // 64 registers); every chunk re-reads the B fragments of its columns from shared memory
@@ -148,7 +174,7 @@ __device__ __forceinline__ void mode_product_dmma(const double *__restrict__ M, 
             for (int u = 0; u < 2; ++u) {
                 const int col = ct * 8 + 2 * ak + u;
                 if (col < ncols) {
-                    const int c = mdiv(col, mg_left), a = col - c * left;
+                    const int c = mdivT<BIG>(col, mg_left), a = col - c * left;
                     double *y = out + a + left * n_out * c;
 #pragma unroll
                     for (int t = 0; t < EVR_DMMA_ROWCHUNK; ++t) {
@@ -161,14 +187,15 @@ __device__ __forceinline__ void mode_product_dmma(const double *__restrict__ M, 
     }
 }
 // dispatcher: DMMA for the large modes (whole warps only), DFMA otherwise
+template <bool BIG = false>
 __device__ __forceinline__ void mode_product_any(const double *__restrict__ M, int n_out, int n_in,
                                                  const double *in, double *out, int left, int right,
                                                  const unsigned mg_left, const unsigned mg_lo, const int use_dmma)
 {
     if (use_dmma && n_out >= EVR_DMMA_MIN && n_in >= EVR_DMMA_MIN && n_out <= 8 * EVR_DMMA_MAXROWT && (blockDim.x & 31) == 0)
-        mode_product_dmma(M, n_out, n_in, in, out, left, right, mg_left);
+        mode_product_dmma<BIG>(M, n_out, n_in, in, out, left, right, mg_left);
     else
-        mode_product(M, n_out, n_in, in, out, left, right, mg_left, mg_lo);
+        mode_product<BIG>(M, n_out, n_in, in, out, left, right, mg_left, mg_lo);
 }
 
 // ---- generic term kernel (any type_Op 0/1 term list, any mode sizes that fit) ----------
@@ -177,15 +204,20 @@ __device__ __forceinline__ void mode_product_any(const double *__restrict__ M, i
 // dynamic smem: [2 or 3 * cap doubles][ints: nq_of,nb_of,offB,offG (4*D*(LG+1))][per-term ints 5*D + 3*(D+1)]
 //               [3 ints per operator term]
 #define EVR_GEN_SMEM_INTS(nT, D, nop) (4 * (nT) + 5 * (D) + 3 * ((D) + 1) + 3 * (nop))
+// BIG = true: the class of terms that do not fit in shared memory (no such limit in the reference): the two or three work
+// buffers of a CTA live in its slice of Cc.scratch (global memory, L2-resident for all but enormous terms) and the index
+// divisions are exact for any term size; everything else is the same code.
+template <bool BIG>
 static __global__ void __launch_bounds__(256, 4)
 sg4_term_kernel_generic(const PlanDev P, const GenClassDev Cc, const int npsi,
                         const double *__restrict__ psi, double *__restrict__ Hpsi)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    double *bufA = reinterpret_cast<double *>(smem_raw);
+    const int nbuf = Cc.dcache ? 3 : 2;
+    double *bufA = BIG ? Cc.scratch + (size_t)blockIdx.x * nbuf * Cc.cap : reinterpret_cast<double *>(smem_raw);
     double *bufB = bufA + Cc.cap;
     double *bufC = bufB + Cc.cap;                  // only with Cc.dcache
-    int *s_nq_of = reinterpret_cast<int *>(bufB + (Cc.dcache ? 2 : 1) * Cc.cap);
+    int *s_nq_of = BIG ? reinterpret_cast<int *>(smem_raw) : reinterpret_cast<int *>(bufA + (size_t)nbuf * Cc.cap);
     const int nT = P.D * (P.LG + 1);
     int *s_nb_of = s_nq_of + nT;
     int *s_offB  = s_nb_of + nT;
@@ -218,18 +250,18 @@ sg4_term_kernel_generic(const PlanDev P, const GenClassDev Cc, const int npsi,
     for (long long w = blockIdx.x; w < n_items; w += gridDim.x) {
         const int it = (int)(w / npsi);
         const int ip_only = (int)(w - (long long)it * npsi);
-        const TermDev T = P.terms[Cc.term_begin + it];
+        const TermDev T = P.terms[Cc.list ? Cc.list[Cc.term_begin + it] : Cc.term_begin + it];
         const uint8_t *lev = P.lev + T.lev_off;
         __syncthreads();               // previous term fully done before the per-term tables change
         for (int k = threadIdx.x; k <= D; k += blockDim.x) {
             int strq = 1, strb = 1;    // grid / basis stride of mode k (first mode fastest)
             for (int j = 0; j < k; ++j) { strq *= s_nq_of[j * (P.LG + 1) + lev[j]]; strb *= s_nb_of[j * (P.LG + 1) + lev[j]]; }
-            s_mgq[k] = magic_of(strq); s_mgb[k] = magic_of(strb);
+            s_mgq[k] = magic_ofT<BIG>(strq); s_mgb[k] = magic_ofT<BIG>(strb);
             if (k < D) {
                 const int i = k * (P.LG + 1) + lev[k];
                 s_tnq[k] = s_nq_of[i]; s_tnb[k] = s_nb_of[i];
                 s_oB[k] = s_offB[i];   s_oG[k] = s_offG[i];
-                s_str[k] = strq;       s_mgn[k] = magic_of(s_nq_of[i]);
+                s_str[k] = strq;       s_mgn[k] = magic_ofT<BIG>(s_nq_of[i]);
             }
         }
         // pull the term's slices of the operator grids into L2 while the gather and the B->G passes run
@@ -265,7 +297,7 @@ sg4_term_kernel_generic(const PlanDev P, const GenClassDev Cc, const int npsi,
                     const int nbk = s_tnb[k], nqk = s_tnq[k];
                     right /= nbk;
                     if (nbk == 1 && nqk == 1) continue;        // scalar folded into T.wfold by the plan
-                    mode_product_any(P.B + s_oB[k], nqk, nbk, cur, oth, left, right, s_mgq[k], s_mgq[k + 1], P.use_dmma);
+                    mode_product_any<BIG>(P.B + s_oB[k], nqk, nbk, cur, oth, left, right, s_mgq[k], s_mgq[k + 1], P.use_dmma);
                     double *t = cur; cur = oth; oth = t;
                     left *= nqk;
                     __syncthreads();
@@ -305,28 +337,22 @@ sg4_term_kernel_generic(const PlanDev P, const GenClassDev Cc, const int npsi,
                         const int k = (m1 >= 0) ? m1 : m2;
                         const double *M = ((m1 == m2) ? P.D2 : P.D1) + s_oG[k];
                         const int n = s_tnq[k], st = s_str[k];
-                        const int qd = mdiv(q, s_mgq[k]);
-                        const int qk = qd - mdiv(qd, s_mgn[k]) * n;
+                        const int qd = mdivT<BIG>(q, s_mgq[k]);
+                        const int qk = qd - mdivT<BIG>(qd, s_mgn[k]) * n;
                         const int base = q - qk * st;
 #pragma unroll
-                        for (int j = 0; j < EVR_MAXCH; ++j) if (j < nb0) {
-                            double s = 0.0;
-                            for (int b = 0; b < n; ++b) s = fma(__ldg(M + qk + n * b), cur[j * nq + base + b * st], s);
-                            d[j] = s;
-                        }
+                        for (int j = 0; j < EVR_MAXCH; ++j) if (j < nb0) d[j] = dot4(M + qk, n, cur + j * nq + base, st, n);
                     } else {
                         const double *Ma = P.D1 + s_oG[m1], *Mb = P.D1 + s_oG[m2];
                         const int na = s_tnq[m1], sa = s_str[m1], nbb = s_tnq[m2], sb = s_str[m2];
-                        const int qda = mdiv(q, s_mgq[m1]), qdb = mdiv(q, s_mgq[m2]);
-                        const int qa = qda - mdiv(qda, s_mgn[m1]) * na, qb = qdb - mdiv(qdb, s_mgn[m2]) * nbb;
+                        const int qda = mdivT<BIG>(q, s_mgq[m1]), qdb = mdivT<BIG>(q, s_mgq[m2]);
+                        const int qa = qda - mdivT<BIG>(qda, s_mgn[m1]) * na, qb = qdb - mdivT<BIG>(qdb, s_mgn[m2]) * nbb;
                         const int base = q - qa * sa - qb * sb;
 #pragma unroll
                         for (int j = 0; j < EVR_MAXCH; ++j) if (j < nb0) {
                             double s = 0.0;
                             for (int b2 = 0; b2 < nbb; ++b2) {
-                                double s1 = 0.0;
-                                for (int b1 = 0; b1 < na; ++b1)
-                                    s1 = fma(__ldg(Ma + qa + na * b1), cur[j * nq + base + b1 * sa + b2 * sb], s1);
+                                const double s1 = dot4(Ma + qa, na, cur + j * nq + base + b2 * sb, sa, na);
                                 s = fma(__ldg(Mb + qb + nbb * b2), s1, s);
                             }
                             d[j] = s;
@@ -347,13 +373,10 @@ sg4_term_kernel_generic(const PlanDev P, const GenClassDev Cc, const int npsi,
                     const int na = s_tnq[a], sa = s_str[a];
                     const double *Ma = P.D1 + s_oG[a];
                     for (int o = threadIdx.x; o < nq * nb0; o += blockDim.x) {
-                        const int j = mdiv(o, s_mgq[D]), q = o - j * nq;
-                        const int qda = mdiv(q, s_mgq[a]);
-                        const int qa = qda - mdiv(qda, s_mgn[a]) * na;
-                        const double *x = cur + j * nq + (q - qa * sa);
-                        double g = 0.0;
-                        for (int b = 0; b < na; ++b) g = fma(__ldg(Ma + qa + na * b), x[b * sa], g);
-                        bufC[o] = g;
+                        const int j = mdivT<BIG>(o, s_mgq[D]), q = o - j * nq;
+                        const int qda = mdivT<BIG>(q, s_mgq[a]);
+                        const int qa = qda - mdivT<BIG>(qda, s_mgn[a]) * na;
+                        bufC[o] = dot4(Ma + qa, na, cur + j * nq + (q - qa * sa), sa, na);
                     }
                     __syncthreads();
                     const int t0 = P.sweep_begin[sw], t1 = P.sweep_begin[sw + 1];
@@ -370,15 +393,11 @@ sg4_term_kernel_generic(const PlanDev P, const GenClassDev Cc, const int npsi,
                             } else {
                                 const double *Mb = P.D1 + s_oG[m2];
                                 const int nbb = s_tnq[m2], sb = s_str[m2];
-                                const int qdb = mdiv(q, s_mgq[m2]);
-                                const int qb = qdb - mdiv(qdb, s_mgn[m2]) * nbb;
+                                const int qdb = mdivT<BIG>(q, s_mgq[m2]);
+                                const int qb = qdb - mdivT<BIG>(qdb, s_mgn[m2]) * nbb;
                                 const int base = q - qb * sb;
 #pragma unroll
-                                for (int j = 0; j < EVR_MAXCH; ++j) if (j < nb0) {
-                                    double s = 0.0;
-                                    for (int b2 = 0; b2 < nbb; ++b2) s = fma(__ldg(Mb + qb + nbb * b2), bufC[j * nq + base + b2 * sb], s);
-                                    d[j] = s;
-                                }
+                                for (int j = 0; j < EVR_MAXCH; ++j) if (j < nb0) d[j] = dot4(Mb + qb, nbb, bufC + j * nq + base, sb, nbb);
                             }
                             add_term(t, d, acc, q);
                         }
@@ -396,7 +415,7 @@ sg4_term_kernel_generic(const PlanDev P, const GenClassDev Cc, const int npsi,
                     const int nbk = s_tnb[k], nqk = s_tnq[k];
                     right /= nqk;
                     if (nbk == 1 && nqk == 1) continue;
-                    mode_product_any(P.BTw + s_oB[k], nbk, nqk, cur, oth, left, right, s_mgb[k], s_mgb[k + 1], P.use_dmma);
+                    mode_product_any<BIG>(P.BTw + s_oB[k], nbk, nqk, cur, oth, left, right, s_mgb[k], s_mgb[k + 1], P.use_dmma);
                     double *t = cur; cur = oth; oth = t;
                     left *= nbk;
                     __syncthreads();
@@ -549,9 +568,7 @@ sg4_term_kernel_type10(const PlanDev P, const Op10Dev O, const int npsi,
             const int qd = mdiv(q, s_mgs[k]);                        // no integer division per point
             const int qk = qd - mdiv(qd, s_mgn[k]) * nk;
             const int base = q - qk * st;
-            double s = 0.0;
-            for (int b = 0; b < nk; ++b) s = fma(__ldg(M + qk + nk * b), arr[base + b * st], s);
-            return s;
+            return dot4(M + qk, nk, arr + base, st, nk);
         };
         for (int c = 0; c < nb0; ++c) {
             // phi = psi_c * sq  -> chi buffer

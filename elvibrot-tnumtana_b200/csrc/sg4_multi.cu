@@ -260,7 +260,7 @@ int64_t evr::multi_info(const evr_sg4_plan *p, int what)
     case EVR_INFO_LAUNCHES:
         for (auto *s : p->sub) sum += evr_sg4_plan_info(s, what);
         return sum + p->multi_launches;
-    case EVR_INFO_NQ_LOCAL: case EVR_INFO_S_LOCAL: case EVR_INFO_FLOPS_NPSI1:
+    case EVR_INFO_NQ_LOCAL: case EVR_INFO_S_LOCAL: case EVR_INFO_FLOPS_NPSI1: case EVR_INFO_GENERIC_TERMS:
         for (auto *s : p->sub) sum += evr_sg4_plan_info(s, what);
         return sum;
     case EVR_INFO_ALG_BYTES_NPSI1: case EVR_INFO_ALG_BYTES_PER_RHS_EXTRA: {

@@ -13,6 +13,7 @@
 #include "sg4_plan.h"
 
 #include <algorithm>
+#include <cstdlib>
 #include <string>
 
 using evr::fail;
@@ -22,14 +23,17 @@ namespace evr {
 enum { NESTED_BTOG = 0, NESTED_GTOB = 1, NESTED_DERIV = 2 };
 
 // dynamic smem: bufA[cap] | bufB[cap] | ints: nq_of, nb_of, offB, offG (4*D*(LG+1)) | per-term ints 5*D | magic 3*(D+1)
+// BIG = true: terms [term_begin, term_begin + n_terms) do not fit in shared memory; the two buffers of a CTA live in its
+// slice of `scratch` (global memory) and the index divisions are exact for any size (sg4_kernels.cuh: mdivT)
+template <bool BIG>
 static __global__ void __launch_bounds__(256, 2)
 sg4_nested_kernel(const PlanDev P, const int mode, const int nvec, const double *__restrict__ in, double *__restrict__ out,
-                  const int der1, const int der2)
+                  const int der1, const int der2, const int term_begin, const int n_terms, const int cap, double *scratch)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    double *bufA = reinterpret_cast<double *>(smem_raw);
-    double *bufB = bufA + P.cap;
-    int *s_nq_of = reinterpret_cast<int *>(bufB + P.cap);
+    double *bufA = BIG ? scratch + (size_t)blockIdx.x * 2 * cap : reinterpret_cast<double *>(smem_raw);
+    double *bufB = bufA + cap;
+    int *s_nq_of = BIG ? reinterpret_cast<int *>(smem_raw) : reinterpret_cast<int *>(bufB + cap);
     const int nT = P.D * (P.LG + 1);
     int *s_nb_of = s_nq_of + nT;
     int *s_offB  = s_nb_of + nT;
@@ -49,22 +53,22 @@ sg4_nested_kernel(const PlanDev P, const int mode, const int nvec, const double 
     __syncthreads();
     const int D = P.D, nb0 = P.nb0;
     const long long lenB = P.nb * nb0, lenG = P.NQ_local * nb0;
-    const long long n_items = (long long)P.n_terms * nvec;
+    const long long n_items = (long long)n_terms * nvec;
     for (long long w = blockIdx.x; w < n_items; w += gridDim.x) {
         const int it = (int)(w / nvec);
         const int iv = (int)(w - (long long)it * nvec);
-        const TermDev T = P.terms[it];
+        const TermDev T = P.terms[term_begin + it];
         const uint8_t *lev = P.lev + T.lev_off;
         __syncthreads();
         for (int k = threadIdx.x; k <= D; k += blockDim.x) {
             int strq = 1, strb = 1;
             for (int j = 0; j < k; ++j) { strq *= s_nq_of[j * (P.LG + 1) + lev[j]]; strb *= s_nb_of[j * (P.LG + 1) + lev[j]]; }
-            s_mgq[k] = magic_of(strq); s_mgb[k] = magic_of(strb);
+            s_mgq[k] = magic_ofT<BIG>(strq); s_mgb[k] = magic_ofT<BIG>(strb);
             if (k < D) {
                 const int i = k * (P.LG + 1) + lev[k];
                 s_tnq[k] = s_nq_of[i]; s_tnb[k] = s_nb_of[i];
                 s_oB[k] = s_offB[i];   s_oG[k] = s_offG[i];
-                s_str[k] = strq;       s_mgn[k] = magic_of(s_nq_of[i]);
+                s_str[k] = strq;       s_mgn[k] = magic_ofT<BIG>(s_nq_of[i]);
             }
         }
         __syncthreads();
@@ -86,7 +90,7 @@ sg4_nested_kernel(const PlanDev P, const int mode, const int nvec, const double 
                 const int nbk = s_tnb[k], nqk = s_tnq[k];
                 right /= nbk;
                 if (nbk == 1 && nqk == 1) { fold *= __ldg(P.B + s_oB[k]); continue; }
-                mode_product_any(P.B + s_oB[k], nqk, nbk, cur, oth, left, right, s_mgq[k], s_mgq[k + 1], P.use_dmma);
+                mode_product_any<BIG>(P.B + s_oB[k], nqk, nbk, cur, oth, left, right, s_mgq[k], s_mgq[k + 1], P.use_dmma);
                 double *t = cur; cur = oth; oth = t;
                 left *= nqk;
                 __syncthreads();
@@ -94,7 +98,7 @@ sg4_nested_kernel(const PlanDev P, const int mode, const int nvec, const double 
             // SmolyakRep2_TO_tabR1bis: RVecG((ib0-1)*NQ + offset(iG) + q)
             double *y = out + (long long)iv * lenG + T.grid_off;
             for (int o = threadIdx.x; o < nq * nb0; o += blockDim.x) {
-                const int c = mdiv(o, s_mgq[D]), q = o - c * nq;
+                const int c = mdivT<BIG>(o, s_mgq[D]), q = o - c * nq;
                 y[(long long)c * P.NQ_local + q] = fold * cur[o];
             }
         } else if (mode == NESTED_GTOB) {
@@ -102,7 +106,7 @@ sg4_nested_kernel(const PlanDev P, const int mode, const int nvec, const double 
             if (fabs(T.weight) < 1e-6) continue;
             const double *x = in + (long long)iv * lenG + T.grid_off;
             for (int o = threadIdx.x; o < nq * nb0; o += blockDim.x) {
-                const int c = mdiv(o, s_mgq[D]), q = o - c * nq;
+                const int c = mdivT<BIG>(o, s_mgq[D]), q = o - c * nq;
                 cur[o] = __ldg(x + (long long)c * P.NQ_local + q);
             }
             __syncthreads();
@@ -112,7 +116,7 @@ sg4_nested_kernel(const PlanDev P, const int mode, const int nvec, const double 
                 const int nbk = s_tnb[k], nqk = s_tnq[k];
                 right /= nqk;
                 if (nbk == 1 && nqk == 1) { fold *= __ldg(P.BTw + s_oB[k]); continue; }
-                mode_product_any(P.BTw + s_oB[k], nbk, nqk, cur, oth, left, right, s_mgb[k], s_mgb[k + 1], P.use_dmma);
+                mode_product_any<BIG>(P.BTw + s_oB[k], nbk, nqk, cur, oth, left, right, s_mgb[k], s_mgb[k + 1], P.use_dmma);
                 double *t = cur; cur = oth; oth = t;
                 left *= nbk;
                 __syncthreads();
@@ -128,7 +132,7 @@ sg4_nested_kernel(const PlanDev P, const int mode, const int nvec, const double 
             // one mode, d1 d1 for two modes, d1 for one index (...SG4.f90:2690-2795)
             double *y = out + (long long)iv * lenG + T.grid_off;
             for (int o = threadIdx.x; o < nq * nb0; o += blockDim.x) {
-                const int c = mdiv(o, s_mgq[D]), q = o - c * nq;
+                const int c = mdivT<BIG>(o, s_mgq[D]), q = o - c * nq;
                 cur[o] = y[(long long)c * P.NQ_local + q];
             }
             __syncthreads();
@@ -138,12 +142,12 @@ sg4_nested_kernel(const PlanDev P, const int mode, const int nvec, const double 
                 else { k = pass ? der2 : der1; if (k < 0) continue; M = P.D1 + s_oG[k]; }
                 const int n = s_tnq[k];
                 int left = s_str[k], right = (nq / (left * n)) * nb0;
-                mode_product_any(M, n, n, cur, oth, left, right, s_mgq[k], s_mgq[k + 1], P.use_dmma);
+                mode_product_any<BIG>(M, n, n, cur, oth, left, right, s_mgq[k], s_mgq[k + 1], P.use_dmma);
                 double *t = cur; cur = oth; oth = t;
                 __syncthreads();
             }
             for (int o = threadIdx.x; o < nq * nb0; o += blockDim.x) {
-                const int c = mdiv(o, s_mgq[D]), q = o - c * nq;
+                const int c = mdivT<BIG>(o, s_mgq[D]), q = o - c * nq;
                 y[(long long)c * P.NQ_local + q] = cur[o];
             }
         }
@@ -156,21 +160,39 @@ static int nested_launch(evr_sg4_plan *p, int mode, int nvec, const double *d_in
 {
     if (p->n_terms == 0) return 0;
     const int nT = p->D * (p->LG + 1);
-    const size_t smem = (size_t)2 * p->cap * sizeof(double) + (size_t)(4 * nT + 5 * p->D + 3 * (p->D + 1)) * sizeof(int);
+    const size_t ints = (size_t)(4 * nT + 5 * p->D + 3 * (p->D + 1)) * sizeof(int);
+    // the terms beyond the shared-memory budget come first in work order (sg4_plan.cu: gen_class_of): global work buffers
+    const int n_big = p->n_big_terms, n_small = p->n_terms - n_big;
+    if (n_big > 0) {
+        const size_t per_cta = (size_t)2 * p->cap * sizeof(double);
+        const char *e = getenv("EVR_SG4_SCRATCH_MB");
+        const size_t budget = (size_t)(e ? std::max(1, atoi(e)) : 4096) << 20;
+        const int cmax = (int)std::min<size_t>((size_t)p->sm_count * 2, std::max<size_t>(1, budget / per_cta));
+        if (!p->d_nscratch) {
+            if (cudaMalloc((void **)&p->d_nscratch, per_cta * cmax) != cudaSuccess) { cudaGetLastError(); return fail("evr_sg4 nested: cannot allocate the work buffers of the large terms"); }
+        }
+        const long long items = (long long)n_big * nvec;
+        const int ctas = (int)std::max<long long>(1, std::min<long long>(items, cmax));
+        evr::sg4_nested_kernel<true><<<ctas, 256, ints, st>>>(p->pd, mode, nvec, d_in, d_out, der1, der2, 0, n_big, p->cap, p->d_nscratch);
+        if (cudaGetLastError() != cudaSuccess) return fail("evr_sg4 nested: kernel launch failed");
+        p->launches += 1;
+    }
+    if (n_small == 0) return 0;
+    const size_t smem = (size_t)2 * p->cap_small * sizeof(double) + ints;
     if (smem > 227 * 1024) return fail("evr_sg4 nested: shared-memory budget exceeded");
     static size_t attr_max[64] = {0};
     size_t &amax = attr_max[p->device & 63];
     if (smem > amax) {
-        if (cudaFuncSetAttribute(evr::sg4_nested_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+        if (cudaFuncSetAttribute(evr::sg4_nested_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
             return fail("evr_sg4 nested: cudaFuncSetAttribute(smem) failed");
         amax = smem;
     }
     int occ = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, evr::sg4_nested_kernel, 256, smem) != cudaSuccess || occ < 1)
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, evr::sg4_nested_kernel<false>, 256, smem) != cudaSuccess || occ < 1)
         return fail("evr_sg4 nested: kernel cannot be resident");
-    const long long items = (long long)p->n_terms * nvec;
+    const long long items = (long long)n_small * nvec;
     const int ctas = (int)std::max<long long>(1, std::min<long long>(items, (long long)p->sm_count * occ));
-    evr::sg4_nested_kernel<<<ctas, 256, smem, st>>>(p->pd, mode, nvec, d_in, d_out, der1, der2);
+    evr::sg4_nested_kernel<false><<<ctas, 256, smem, st>>>(p->pd, mode, nvec, d_in, d_out, der1, der2, n_big, n_small, p->cap_small, nullptr);
     if (cudaGetLastError() != cudaSuccess) return fail("evr_sg4 nested: kernel launch failed");
     p->launches += 1;
     return 0;

@@ -48,29 +48,69 @@ static int upload(T **dptr, const T *h, size_t n)
 
 // Size classes of the generic kernel: CTA threads 256 / 128 / 64 / 32 for terms of > 768 / > 192 / > 48 / <= 48
 // values.  Classes of larger terms get a third shared-memory buffer for the mixed-derivative sweeps
-// (want_cache: the operator has mixed terms) when it fits.
-static int gen_class_of(int64_t tsize) { return tsize > 768 ? 0 : (tsize > 192 ? 1 : (tsize > 48 ? 2 : 3)); }
-static int gen_configure(evr_sg4_plan *p, bool want_cache, int n_opterms)
+// (want_cache: the operator has mixed terms) when it fits.  Class 0 ("big") holds the terms whose two work buffers do
+// not fit in shared memory at all: their buffers live in global memory (sg4_kernels.cuh, BIG instantiation), so that a
+// term may be as large as the reference allows (its RDP arrays are heap-allocated, no limit).
+#define EVR_GEN_BIG_BYTES (200 * 1024)
+static int gen_class_of(int64_t tsize, int nb0)
 {
-    static const int class_threads[4] = {256, 128, 64, 32};
+    if (tsize * nb0 * 2 * (int64_t)sizeof(double) > EVR_GEN_BIG_BYTES) return 0;
+    return tsize > 768 ? 1 : (tsize > 192 ? 2 : (tsize > 48 ? 3 : 4));
+}
+// One set of generic-kernel launches: the size classes of either all terms of the plan (list == nullptr: contiguous
+// ranges of the work order) or of the terms listed by work-order index (the remainder of a fast-path plan).
+struct GenSet {
+    int *n; evr::GenClassDev *cls; int *threads; int *occ; size_t *smem; bool *big; double **scratch; int **d_list;
+};
+static int gen_configure_set(evr_sg4_plan *p, bool want_cache, int n_opterms, const std::vector<int> *list, GenSet G)
+{
+    static const int class_threads[5] = {256, 256, 128, 64, 32};
     const int nT = p->D * (p->LG + 1);
-    int cache_classes = 4;                                  // every class (measured best: profiles/shape_bench_r1_generic_v2.txt)
-    if (getenv("EVR_SG4_DCACHE")) cache_classes = atoi(getenv("EVR_SG4_DCACHE"));
-    p->n_gclasses = 0;
+    int cache_classes = 5;                                  // every class (measured best: profiles/shape_bench_r1_generic_v2.txt)
+    if (getenv("EVR_SG4_DCACHE")) cache_classes = atoi(getenv("EVR_SG4_DCACHE")) + 1;
+    *G.n = 0;
     size_t smem_max = 0;
     int w0 = 0;
-    for (int c = 0; c < 4; ++c) {
+    const int n_all = list ? (int)list->size() : p->n_terms;
+    auto tsize_at = [&](int w) { return p->h_tsize[p->order[list ? (*list)[w] : w]]; };
+    const size_t ints = (size_t)EVR_GEN_SMEM_INTS(nT, p->D, n_opterms) * sizeof(int);
+    if (ints > 40 * 1024) return fail("evr_sg4: too many operator terms / levels for the per-CTA tables");
+    if (*G.scratch) { cudaFree(*G.scratch); *G.scratch = nullptr; }
+    if (G.d_list && *G.d_list) { cudaFree(*G.d_list); *G.d_list = nullptr; }
+    if (list && n_all > 0 && upload(G.d_list, list->data(), list->size())) return 1;
+    for (int c = 0; c < 5; ++c) {
         int w1 = w0;
         int64_t ccap = 1;
-        while (w1 < p->n_terms && gen_class_of(p->h_tsize[p->order[w1]]) == c) { ccap = std::max(ccap, p->h_tsize[p->order[w1]] * p->nb0); ++w1; }
+        while (w1 < n_all && gen_class_of(tsize_at(w1), p->nb0) == c) { ccap = std::max(ccap, tsize_at(w1) * p->nb0); ++w1; }
         if (w1 == w0) continue;
-        const int g = p->n_gclasses++;
-        const size_t ints = (size_t)EVR_GEN_SMEM_INTS(nT, p->D, n_opterms) * sizeof(int);
-        bool dc = want_cache && c < cache_classes && (size_t)3 * ccap * sizeof(double) + ints <= 227 * 1024;
-        p->gclass[g].term_begin = w0; p->gclass[g].n_terms = w1 - w0; p->gclass[g].cap = (int)ccap; p->gclass[g].dcache = dc ? 1 : 0;
-        p->gclass_threads[g] = class_threads[c];
-        p->gclass_smem[g] = (size_t)(dc ? 3 : 2) * ccap * sizeof(double) + ints;
-        smem_max = std::max(smem_max, p->gclass_smem[g]);
+        const int g = (*G.n)++;
+        const bool big = (c == 0);
+        bool dc = want_cache && c < cache_classes && (big || (size_t)3 * ccap * sizeof(double) + ints <= 227 * 1024);
+        G.cls[g].term_begin = w0; G.cls[g].n_terms = w1 - w0; G.cls[g].cap = (int)ccap; G.cls[g].dcache = dc ? 1 : 0;
+        G.cls[g].scratch = nullptr;
+        G.cls[g].list = list ? *G.d_list : nullptr;
+        G.threads[g] = class_threads[c];
+        G.big[g] = big;
+        if (big) {
+            // global work buffers: as many CTAs as the scratch budget allows (EVR_SG4_SCRATCH_MB, default 4096), at most 4 per SM
+            if (ccap >= (int64_t)1 << 30) return fail("evr_sg4: a Smolyak term has more than 2^30 values");
+            const size_t per_cta = (size_t)(dc ? 3 : 2) * ccap * sizeof(double);
+            const char *e = getenv("EVR_SG4_SCRATCH_MB");
+            const size_t budget = (size_t)(e ? std::max(1, atoi(e)) : 4096) << 20;
+            int ctas = (int)std::min<size_t>((size_t)p->sm_count * 4, std::max<size_t>(1, budget / per_cta));
+            ctas = std::min(ctas, std::max(1, (w1 - w0) * 32));     // never more CTAs than a 32-vector block of these terms can use
+            G.smem[g] = ints;
+            G.occ[g] = -ctas;                                // negative: absolute CTA count, not per SM
+            if (cudaMalloc((void **)G.scratch, per_cta * ctas) != cudaSuccess) {
+                cudaGetLastError();
+                return fail("evr_sg4: cannot allocate the work buffers of the terms that exceed shared memory (" +
+                            std::to_string((per_cta * ctas) >> 20) + " MB)");
+            }
+            G.cls[g].scratch = *G.scratch;
+        } else {
+            G.smem[g] = (size_t)(dc ? 3 : 2) * ccap * sizeof(double) + ints;
+            smem_max = std::max(smem_max, G.smem[g]);
+        }
         w0 = w1;
     }
     if (smem_max > 227 * 1024) return fail("evr_sg4: shared-memory budget exceeded");
@@ -78,17 +118,31 @@ static int gen_configure(evr_sg4_plan *p, bool want_cache, int n_opterms)
     static size_t attr_max[64] = {0};
     size_t &amax = attr_max[p->device & 63];
     amax = std::max(amax, smem_max);
-    if (cudaFuncSetAttribute(evr::sg4_term_kernel_generic, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)amax) != cudaSuccess)
+    if (cudaFuncSetAttribute(evr::sg4_term_kernel_generic<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)amax) != cudaSuccess)
         return fail("evr_sg4: cudaFuncSetAttribute(smem) failed");
-    for (int g = 0; g < p->n_gclasses; ++g) {
+    for (int g = 0; g < *G.n; ++g) {
+        if (G.big[g]) continue;
         int occ = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, evr::sg4_term_kernel_generic, p->gclass_threads[g], p->gclass_smem[g]) != cudaSuccess || occ < 1)
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, evr::sg4_term_kernel_generic<false>, G.threads[g], G.smem[g]) != cudaSuccess || occ < 1)
             return fail("evr_sg4: generic kernel cannot be resident (occupancy 0)");
-        p->gclass_occ[g] = occ;
+        G.occ[g] = occ;
     }
-    p->gen_ctas_max = p->n_gclasses ? p->sm_count * p->gclass_occ[0] : p->sm_count;
+    return 0;
+}
+static int gen_configure(evr_sg4_plan *p, bool want_cache, int n_opterms)
+{
+    GenSet G{&p->n_gclasses, p->gclass, p->gclass_threads, p->gclass_occ, p->gclass_smem, p->gclass_big, &p->d_gscratch, nullptr};
+    if (gen_configure_set(p, want_cache, n_opterms, nullptr, G)) return 1;
+    auto ctas_of = [&](int g) { return p->gclass_occ[g] < 0 ? -p->gclass_occ[g] : p->sm_count * p->gclass_occ[g]; };
+    p->gen_ctas_max = p->n_gclasses ? ctas_of(0) : p->sm_count;
     p->grid_ctas = p->n_gclasses ? std::max(1, std::min(p->gclass[0].n_terms, p->gen_ctas_max)) : 1;
     return 0;
+}
+// the terms a fast-path plan cannot take (mode sizes beyond its register tiles, terms beyond its shared-memory budget)
+static int gen_configure_rest(evr_sg4_plan *p, const std::vector<int> &work_list)
+{
+    GenSet G{&p->n_rclasses, p->rclass, p->rclass_threads, p->rclass_occ, p->rclass_smem, p->rclass_big, &p->d_rscratch, &p->d_rlist};
+    return gen_configure_set(p, p->pd.n_sweeps > 0, p->n_opterms, &work_list, G);
 }
 
 extern "C" int evr_sg4_plan_create(evr_sg4_plan **out, int device,
@@ -232,12 +286,8 @@ int evr::plan_create_single(evr_sg4_plan **out, int device,
         wfold[t] = fold; tsize[t] = mx;
     }
     p->flops_npsi1 = flops * nb0;
-    if (cap * nb0 * 2 * (int64_t)sizeof(double) > 220 * 1024) {
-        delete p;
-        return fail("evr_sg4_plan_create: a Smolyak term does not fit in shared memory (max term size*nb0 = " +
-                    std::to_string(cap * nb0) + " doubles)");
-    }
-    p->cap = (int)(cap * nb0);
+    if (cap * nb0 >= (int64_t)1 << 30) { delete p; return fail("evr_sg4_plan_create: a Smolyak term has more than 2^30 values"); }
+    p->cap = (int)(cap * nb0);        // terms beyond the shared-memory budget run in the generic kernel's global-buffer class
     p->h_map.assign(tab_iB + map_start, tab_iB + map_start + p->S_local);
     p->h_map_off.resize(p->n_terms); p->h_grid_off.resize(p->n_terms);
     for (int t = 0; t < p->n_terms; ++t) {
@@ -252,11 +302,17 @@ int evr::plan_create_single(evr_sg4_plan **out, int device,
     p->order.resize(p->n_terms);
     std::iota(p->order.begin(), p->order.end(), 0);
     // size classes of the generic kernel (CTA threads 256 / 128 / 64 / 32), then cost descending inside a class
-    auto gclass_of = [&](int t) { return gen_class_of(tsize[t]); };
+    auto gclass_of = [&](int t) { return gen_class_of(tsize[t], nb0); };
     std::stable_sort(p->order.begin(), p->order.end(), [&](int a, int b) {
         const int ca = gclass_of(a), cb = gclass_of(b);
         return ca != cb ? ca < cb : cost[a] > cost[b];
     });
+
+    p->n_big_terms = 0; p->cap_small = 1;
+    for (int t = 0; t < p->n_terms; ++t) {
+        if (gclass_of(t) == 0) ++p->n_big_terms;
+        else p->cap_small = std::max<int64_t>(p->cap_small, tsize[t] * nb0);
+    }
 
     std::vector<evr::TermDev> terms(p->n_terms);
     std::vector<uint8_t> lev((size_t)p->n_terms * D);
@@ -294,8 +350,7 @@ int evr::plan_create_single(evr_sg4_plan **out, int device,
         if (!ok_ev) { evr_sg4_plan_destroy(&p); return fail("evr_sg4_plan_create: side stream/event creation failed"); }
     }
 
-    p->smem_bytes = (size_t)2 * p->cap * sizeof(double) + (size_t)(4 * nT + 5 * D) * sizeof(int);
-    if (p->smem_bytes > 227 * 1024) { evr_sg4_plan_destroy(&p); return fail("evr_sg4_plan_create: shared-memory budget exceeded"); }
+    p->smem_bytes = (size_t)2 * p->cap * sizeof(double) + (size_t)(4 * nT + 5 * D) * sizeof(int);   // of the largest term (informational)
     p->h_tsize = tsize;
     if (gen_configure(p, false, 0)) { evr_sg4_plan_destroy(&p); return 1; }
 
@@ -335,6 +390,7 @@ static int build_fast_path(evr_sg4_plan *p, int nb_Term, const int32_t *term_mod
                            const double *Mat_cte, const double *const *grids)
 {
     p->fast = false;
+    p->n_rclasses = 0; p->n_rest_terms = 0;
     if (getenv("EVR_SG4_FORCE_GENERIC")) return 0;
     const int D = p->D, LG = p->LG, nb0 = p->nb0, nT = D * (LG + 1);
     for (int i = 0; i < nT; ++i) if (p->h_nq_of[i] != p->h_nb_of[i]) return 0;
@@ -399,7 +455,7 @@ static int build_fast_path(evr_sg4_plan *p, int nb_Term, const int32_t *term_mod
         for (int i = 0; i < nT && iso; ++i) {
             const int n = p->h_nq_of[i];
             if (n < 2) continue;
-            if (n > EVR_ISO_NMAX) { iso = false; break; }
+            if (n > EVR_ISO_NMAX) continue;                 // such a mode never runs in the constant-matrix instantiation
             if (off_of_n[n] < 0) off_of_n[n] = moff[i];
             else if (off_of_n[n] != moff[i]) iso = false;
             any = true;
@@ -415,9 +471,15 @@ static int build_fast_path(evr_sg4_plan *p, int nb_Term, const int32_t *term_mod
     // (<= EVR_RT_NMAX) sends the whole term to the runtime-size instantiation (classes 3..5)
     // iso plans: a term runs in the constant-matrix instantiation when its active mode sizes are 3, 5, 7, 9 or 11; the
     // few other terms of such a plan use the pool-based instantiations like the terms of a non-iso plan
-    std::vector<char> term_rt(p->n_terms, 0), term_iso(p->n_terms, 0);
+    // term_gen: the terms this path cannot take -- a mode beyond the register tiles (n > EVR_RT_NMAX), more tile groups
+    // than a descriptor holds, or psi + acc buffers beyond the shared memory of an SM.  They run in the generic kernel
+    // (gen_configure_rest) on the caller's vectors; the plan stays on the fast path for everything else.
+    std::vector<char> term_rt(p->n_terms, 0), term_iso(p->n_terms, 0), term_gen(p->n_terms, 0);
+    const int64_t fast_cap_max = (int64_t)((227 * 1024 - (pool_in_smem ? pool.size() * sizeof(double) : 0) - 2 * sizeof(evr::FastTermDev) - EVR_FAST_MBAR_BYTES) /
+                                           ((nb0 == 1 && getenv("EVR_SG4_V2") && atoi(getenv("EVR_SG4_V2")) != 0) ? 20 : 16)) - 64;
     for (int t = 0; t < p->n_terms; ++t) {
         const int iG = p->iG_begin + t;
+        if ((int64_t)p->h_tab_nq[iG] * nb0 > fast_cap_max || p->h_tab_nq[iG] > 65535) { term_gen[t] = 1; continue; }
         int c3 = 0, c79 = 0, cbad = 0, nact = 0;
         for (int k = 0; k < D; ++k) {
             const int n = p->h_nq_of[k * (LG + 1) + p->h_tab_l[(size_t)iG * D + k]];
@@ -429,7 +491,7 @@ static int build_fast_path(evr_sg4_plan *p, int nb_Term, const int32_t *term_mod
         if (term_iso[t]) continue;
         for (int k = 0; k < D; ++k) {
             const int n = p->h_nq_of[k * (LG + 1) + p->h_tab_l[(size_t)iG * D + k]];
-            if (n > 1 && fast_template_id(n, 0) == 0) { term_rt[t] = 1; if (n > EVR_RT_NMAX) return 0; }
+            if (n > 1 && fast_template_id(n, 0) == 0) { term_rt[t] = 1; if (n > EVR_RT_NMAX) term_gen[t] = 1; }
         }
     }
     // ---- tunables (experiments: environment overrides) ---------------------------------------------------------
@@ -488,9 +550,9 @@ static int build_fast_path(evr_sg4_plan *p, int nb_Term, const int32_t *term_mod
         std::vector<int> in_n, in_ref;          // per internal mode: size, stride in the reference term layout
     };
     std::vector<TermSched> sched(p->n_terms);
-    int ok = 1;
 #pragma omp parallel for schedule(dynamic, 64)
     for (int t = 0; t < p->n_terms; ++t) {
+        if (term_gen[t]) continue;
         const int iG = p->iG_begin + t;
         evr::FastTermDev &F = sched[t].F;
         std::memset(&F, 0, sizeof(F));
@@ -566,11 +628,7 @@ static int build_fast_path(evr_sg4_plan *p, int nb_Term, const int32_t *term_mod
         }
         auto gsize = [&](const Grp &g) { return act[g.a1].n * (g.a2 >= 0 ? act[g.a2].n : 1) * (g.a3 >= 0 ? act[g.a3].n : 1); };
         std::stable_sort(grp.begin(), grp.end(), [&](const Grp &a, const Grp &b) { return gsize(a) > gsize(b); });
-        if ((int)grp.size() > EVR_MAXG) {
-#pragma omp atomic write
-            ok = 0;
-            continue;
-        }
+        if ((int)grp.size() > EVR_MAXG) { term_gen[t] = 1; continue; }
         F.ngroups = (int)grp.size();
         F.weight = wgt; F.vshift = shift;
         // internal mode order and strides
@@ -604,13 +662,17 @@ static int build_fast_path(evr_sg4_plan *p, int nb_Term, const int32_t *term_mod
                 stride *= A3.n;
             }
             Gd.tmpl = term_rt[t] ? 0 : (Gd.n3 == 3 ? EVR_TMPL_CUBE3 : (Gd.n3 == 2 ? EVR_TMPL_CUBE2 : (unsigned short)fast_template_id(Gd.n1, Gd.n2, term_iso[t] != 0)));
-            if (!term_rt[t] && Gd.tmpl == 0) {
-#pragma omp atomic write
-                ok = 0;
-            }
+            if (!term_rt[t] && Gd.tmpl == 0) term_gen[t] = 1;
         }
     }
-    if (!ok) return 0;
+    {
+        std::vector<int> rest;                               // work-order indices (p->order is sorted by generic size class)
+        for (int w = 0; w < p->n_terms; ++w) if (term_gen[p->order[w]]) rest.push_back(w);
+        if ((int)rest.size() == p->n_terms) return 0;
+        if (!rest.empty() && (p->deterministic || (getenv("EVR_SG4_MIXED") && atoi(getenv("EVR_SG4_MIXED")) == 0))) return 0;   // one kernel family stages the entries
+        p->n_rest_terms = (int)rest.size();
+        if (!rest.empty() && gen_configure_rest(p, rest)) return 1;
+    }
     // ---- batches ("super-terms"): Smolyak terms with the SAME schedule (tile groups, matrices, folded weight and
     // shift) are processed together as one work item.  In the internal layout the term index is simply one more (slowest)
     // dimension, so every pass runs over all tiles of all terms of the batch with full warps, one barrier per pass and one
@@ -630,6 +692,7 @@ static int build_fast_path(evr_sg4_plan *p, int nb_Term, const int32_t *term_mod
     {
         std::map<std::string, std::vector<int>> by_key;
         for (int t = 0; t < p->n_terms; ++t) {
+            if (term_gen[t]) continue;
             const evr::FastTermDev &F = sched[t].F;
             std::string k;
             auto put = [&](const void *ptr, size_t n) { k.append(reinterpret_cast<const char *>(ptr), n); };
@@ -1031,6 +1094,32 @@ __global__ void sg4_permute_out_scaled(const int32_t *__restrict__ perm, const l
 
 struct ScaleArgs { bool on; double E0, Esc; };
 
+// the launches of one set of generic-kernel size classes (all terms, or the remainder of a fast-path plan), class tails
+// overlapping on the side streams
+static int launch_generic_set(evr_sg4_plan *p, int ncls, const evr::GenClassDev *cls, const int *threads, const int *occ,
+                              const size_t *smem, const bool *big, int npsi, const double *d_psi, double *d_Hpsi, cudaStream_t st)
+{
+    const bool multi = ncls > 1 && p->ev_fork != nullptr;
+    if (multi) CUDA_TRY(cudaEventRecord(p->ev_fork, st));
+    for (int c = 0; c < ncls; ++c) {
+        cudaStream_t sc = (multi && c > 0) ? p->side[c] : st;
+        if (multi && c > 0) CUDA_TRY(cudaStreamWaitEvent(sc, p->ev_fork, 0));
+        const long long items = (long long)cls[c].n_terms * npsi;
+        const long long cmax = occ[c] < 0 ? -occ[c] : (long long)p->sm_count * occ[c];
+        const int ctas = (int)std::max<long long>(1, std::min<long long>(items, cmax));
+        if (big[c])
+            evr::sg4_term_kernel_generic<true><<<ctas, threads[c], smem[c], sc>>>(p->pd, cls[c], npsi, d_psi, d_Hpsi);
+        else
+            evr::sg4_term_kernel_generic<false><<<ctas, threads[c], smem[c], sc>>>(p->pd, cls[c], npsi, d_psi, d_Hpsi);
+        p->launches += 1;
+        if (multi && c > 0) {
+            CUDA_TRY(cudaEventRecord(p->ev_join[c], sc));
+            CUDA_TRY(cudaStreamWaitEvent(st, p->ev_join[c], 0));
+        }
+    }
+    return 0;
+}
+
 static int launch_direct(evr_sg4_plan *p, int npsi, const double *d_psi_user, double *d_Hpsi_user, cudaStream_t st,
                          const ScaleArgs sc)
 {
@@ -1099,20 +1188,7 @@ static int launch_direct(evr_sg4_plan *p, int npsi, const double *d_psi_user, do
             evr::sg4_term_kernel_type10<<<ctas, 256, p->smem10, st>>>(p->pd, p->o10, npsi, d_psi, d_Hpsi);
             p->launches += 1;
         } else {
-            const bool multi = p->n_gclasses > 1 && p->ev_fork != nullptr;
-            if (multi) CUDA_TRY(cudaEventRecord(p->ev_fork, st));
-            for (int c = 0; c < p->n_gclasses; ++c) {
-                cudaStream_t sc = (multi && c > 0) ? p->side[c] : st;
-                if (multi && c > 0) CUDA_TRY(cudaStreamWaitEvent(sc, p->ev_fork, 0));
-                const long long items = (long long)p->gclass[c].n_terms * npsi;
-                const int ctas = (int)std::max<long long>(1, std::min<long long>(items, (long long)p->sm_count * p->gclass_occ[c]));
-                evr::sg4_term_kernel_generic<<<ctas, p->gclass_threads[c], p->gclass_smem[c], sc>>>(p->pd, p->gclass[c], npsi, d_psi, d_Hpsi);
-                p->launches += 1;
-                if (multi && c > 0) {
-                    CUDA_TRY(cudaEventRecord(p->ev_join[c], sc));
-                    CUDA_TRY(cudaStreamWaitEvent(st, p->ev_join[c], 0));
-                }
-            }
+            if (launch_generic_set(p, p->n_gclasses, p->gclass, p->gclass_threads, p->gclass_occ, p->gclass_smem, p->gclass_big, npsi, d_psi, d_Hpsi, st)) return 1;
         }
         CUDA_TRY(cudaGetLastError());
         if (det) {      // fixed-order sums of the staged entries (all class kernels have joined the stream)
@@ -1122,16 +1198,24 @@ static int launch_direct(evr_sg4_plan *p, int npsi, const double *d_psi_user, do
             CUDA_TRY(cudaGetLastError());
         }
     }
+    // a fast-path plan may leave a few terms to the generic kernel (gen_configure_rest): they work on the caller's vectors
+    // (reference order), after the fast part has been brought back to that order and before the scaling
+    const bool has_rest = p->fast && p->n_rclasses > 0 && p->n_terms > 0;
     if (use_int) {
         const int64_t nvecs = (int64_t)npsi * p->nb0;
-        if (sc.on) {
+        if (sc.on && !has_rest) {
             const int thr = 256;
             const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>((p->nb + thr - 1) / thr, 148 * 16));
             evr::sg4_permute_out_scaled<<<blocks, thr, 0, st>>>(p->d_perm, p->nb, (int)nvecs, sc.E0, sc.Esc, d_psi_user, p->d_Hpsi_int, d_Hpsi_user);
         } else evr::fast_permute(false, p->d_perm, p->nb, (int)nvecs, p->d_Hpsi_int, d_Hpsi_user, st);
         p->launches += 1;
         CUDA_TRY(cudaGetLastError());
-    } else if (sc.on) {
+    }
+    if (has_rest) {
+        if (launch_generic_set(p, p->n_rclasses, p->rclass, p->rclass_threads, p->rclass_occ, p->rclass_smem, p->rclass_big, npsi, d_psi_user, d_Hpsi_user, st)) return 1;
+        CUDA_TRY(cudaGetLastError());
+    }
+    if (sc.on && (!use_int || has_rest)) {
         const long long n = (long long)npsi * p->nb * p->nb0;
         const int thr = 256;
         const int blocks = (int)std::max<long long>(1, std::min<long long>((n + thr - 1) / thr, 148 * 16));
@@ -1303,6 +1387,32 @@ extern "C" int evr_sg4_apply(evr_sg4_plan *p, int npsi, const double *psi, doubl
     const int64_t n = (int64_t)npsi * p->nb * p->nb0;
     if (ranges_overlap(psi, Hpsi, n)) return fail("evr_sg4_apply: psi and Hpsi overlap (the action is not in-place)");
     if (evr::plan_ensure_staging(p, n)) return 1;
+    // Blocks of long vectors (sub_TabOpPsi with a Davidson block): vector v+1 travels to the device and vector v-1 back to
+    // the host while vector v is in the kernels -- three streams, full-duplex PCIe.  Page-locked caller buffers
+    // (evr_sg4_host_register) are needed for the copies to overlap; pageable ones still give the right result.
+    const int64_t nv = p->nb * p->nb0;
+    static const bool no_pipe = getenv("EVR_SG4_PIPELINE") && atoi(getenv("EVR_SG4_PIPELINE")) == 0;
+    if (npsi >= 2 && nv * (int64_t)sizeof(double) >= ((int64_t)1 << 20) && !no_pipe) {
+        if (!p->s_in) {
+            if (cudaStreamCreateWithFlags(&p->s_in, cudaStreamNonBlocking) != cudaSuccess ||
+                cudaStreamCreateWithFlags(&p->s_out, cudaStreamNonBlocking) != cudaSuccess ||
+                cudaEventCreateWithFlags(&p->ev_pin, cudaEventDisableTiming) != cudaSuccess ||
+                cudaEventCreateWithFlags(&p->ev_pout, cudaEventDisableTiming) != cudaSuccess)
+                return fail("evr_sg4_apply: stream/event creation failed");
+        }
+        for (int v = 0; v < npsi; ++v) {
+            CUDA_TRY(cudaMemcpyAsync(p->d_psi + v * nv, psi + v * nv, (size_t)nv * sizeof(double), cudaMemcpyHostToDevice, p->s_in));
+            CUDA_TRY(cudaEventRecord(p->ev_pin, p->s_in));
+            CUDA_TRY(cudaStreamWaitEvent(p->stream, p->ev_pin, 0));
+            if (launch(p, 1, p->d_psi + v * nv, p->d_Hpsi + v * nv, p->stream)) return 1;
+            CUDA_TRY(cudaEventRecord(p->ev_pout, p->stream));
+            CUDA_TRY(cudaStreamWaitEvent(p->s_out, p->ev_pout, 0));
+            CUDA_TRY(cudaMemcpyAsync(Hpsi + v * nv, p->d_Hpsi + v * nv, (size_t)nv * sizeof(double), cudaMemcpyDeviceToHost, p->s_out));
+        }
+        CUDA_TRY(cudaStreamSynchronize(p->s_out));
+        CUDA_TRY(cudaStreamSynchronize(p->stream));
+        return 0;
+    }
     CUDA_TRY(cudaMemcpyAsync(p->d_psi, psi, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, p->stream));
     if (launch(p, npsi, p->d_psi, p->d_Hpsi, p->stream)) return 1;
     CUDA_TRY(cudaMemcpyAsync(Hpsi, p->d_Hpsi, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
@@ -1329,6 +1439,7 @@ extern "C" int64_t evr_sg4_plan_info(const evr_sg4_plan *p, int what)
     case EVR_INFO_PATH: return p->fast ? 1 : 0;
     case EVR_INFO_FLOPS_NPSI1: return p->flops_npsi1;
     case EVR_INFO_ISO: return (p->fast && p->fast_iso) ? 1 : 0;
+    case EVR_INFO_GENERIC_TERMS: return p->fast ? p->n_rest_terms : p->n_terms;
     default: return -1;
     }
 }
@@ -1348,7 +1459,8 @@ extern "C" int evr_sg4_plan_destroy(evr_sg4_plan **pp)
     cudaFree(p->d_fterms); cudaFree(p->d_fmap); cudaFree(p->d_fmats); cudaFree(p->d_fV);
     cudaFree(p->d_fpos); cudaFree(p->d_gmap); cudaFree(p->d_perm); cudaFree(p->d_psi_int); cudaFree(p->d_Hpsi_int);
     cudaFree(p->d_GG); cudaFree(p->d_Jac); cudaFree(p->d_sq);
-    cudaFree(p->d_det_off); cudaFree(p->d_det_ent); cudaFree(p->d_stage); cudaFree(p->d_fcounters);
+    cudaFree(p->d_det_off); cudaFree(p->d_det_ent); cudaFree(p->d_stage); cudaFree(p->d_fcounters); cudaFree(p->d_gscratch); cudaFree(p->d_nscratch); cudaFree(p->d_rscratch); cudaFree(p->d_rlist);
+    if (p->s_in) { cudaStreamDestroy(p->s_in); cudaStreamDestroy(p->s_out); cudaEventDestroy(p->ev_pin); cudaEventDestroy(p->ev_pout); }
     if (p->stream) cudaStreamDestroy(p->stream);
     for (int c = 0; c < EVR_MAX_FCLASSES; ++c) { if (p->side[c]) cudaStreamDestroy(p->side[c]); if (p->ev_join[c]) cudaEventDestroy(p->ev_join[c]); }
     if (p->ev_fork) cudaEventDestroy(p->ev_fork);

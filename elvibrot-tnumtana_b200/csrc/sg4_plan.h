@@ -75,13 +75,27 @@ struct evr_sg4_plan {
     cudaStream_t stream = nullptr;
     cudaStream_t side[EVR_MAX_FCLASSES] = {nullptr};   // class kernels overlap their tails
     cudaEvent_t ev_fork = nullptr, ev_join[EVR_MAX_FCLASSES] = {nullptr};
+    cudaStream_t s_in = nullptr, s_out = nullptr;      // host-buffer blocks: copy-in / copy-out streams (evr_sg4_apply)
+    cudaEvent_t ev_pin = nullptr, ev_pout = nullptr;
     size_t smem_bytes = 0;
     int grid_ctas = 0, gen_ctas_max = 0;
     // generic kernel: one launch per term-size class (CTA of 256/128/64/32 threads)
     int n_gclasses = 0;
-    evr::GenClassDev gclass[4];
-    int gclass_threads[4] = {0}, gclass_occ[4] = {0};
-    size_t gclass_smem[4] = {0};
+    evr::GenClassDev gclass[5];              // [0] may be the class of terms beyond shared memory (global work buffers)
+    int gclass_threads[5] = {0}, gclass_occ[5] = {0};
+    size_t gclass_smem[5] = {0};
+    bool gclass_big[5] = {false};
+    // fast-path plans: the terms left to the generic kernel (work-order indices in d_rlist), same class scheme
+    int n_rclasses = 0, n_rest_terms = 0;
+    evr::GenClassDev rclass[5];
+    int rclass_threads[5] = {0}, rclass_occ[5] = {0};
+    size_t rclass_smem[5] = {0};
+    bool rclass_big[5] = {false};
+    double *d_rscratch = nullptr;
+    int *d_rlist = nullptr;
+    double *d_gscratch = nullptr, *d_nscratch = nullptr;   // global work buffers of the generic / nested kernels (terms beyond shared memory)
+    int n_big_terms = 0;                     // such terms come first in work order
+    int64_t cap_small = 1;                   // largest term*nb0 among the others
     evr::PlanDev pd{};
     int *d_fcounters = nullptr;              // one work counter per fast-path launch (dynamic item scheduling)
     // deterministic mode (EVR_SG4_DETERMINISTIC=1 when the plan is created): staged scatter + ordered collection

@@ -18,7 +18,7 @@ _lib = None
 TAB_NB_SG, TAB_NB, TAB_S, TAB_NQ, TAB_COUNT0, TAB_LMIN = 0, 1, 2, 3, 4, 5
 TAB_TAB_L, TAB_WEIGHT, TAB_TAB_NQ, TAB_TAB_NB, TAB_SUM_NQ, TAB_SUM_NB, TAB_PACKEDB, TAB_MAP = 10, 11, 12, 13, 14, 15, 16, 17
 INFO_LAUNCHES, INFO_ALG_BYTES_NPSI1, INFO_ALG_BYTES_PER_RHS_EXTRA, INFO_NQ_LOCAL, INFO_S_LOCAL = 0, 1, 2, 3, 4
-INFO_SMEM_BYTES, INFO_GRID_CTAS, INFO_PATH, INFO_FLOPS_NPSI1, INFO_ISO, INFO_DEVICES = 5, 6, 7, 8, 9, 10
+INFO_SMEM_BYTES, INFO_GRID_CTAS, INFO_PATH, INFO_FLOPS_NPSI1, INFO_ISO, INFO_DEVICES, INFO_GENERIC_TERMS = 5, 6, 7, 8, 9, 10, 11
 
 EXPORTS = [
     "evr_sg4_version", "evr_sg4_last_error",

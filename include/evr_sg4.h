@@ -215,7 +215,8 @@ enum {                           /* 'what' for evr_sg4_plan_info */
     EVR_INFO_PATH            = 7,   /* 0 = generic term kernel, 1 = constant-KEO fast path */
     EVR_INFO_FLOPS_NPSI1     = 8,   /* algorithmic flops of one H|psi>      */
     EVR_INFO_ISO             = 9,   /* 1 = fast path runs its constant-matrix instantiation (all modes of a size share one 1-D basis) */
-    EVR_INFO_DEVICES         = 10   /* number of devices the plan spans (evr_sg4_set_devices) */
+    EVR_INFO_DEVICES         = 10,  /* number of devices the plan spans (evr_sg4_set_devices) */
+    EVR_INFO_GENERIC_TERMS   = 11   /* Smolyak terms of the plan that run in the generic kernel (all of them when PATH = 0) */
 };
 int64_t evr_sg4_plan_info(const evr_sg4_plan *plan, int what);
 int     evr_sg4_plan_destroy(evr_sg4_plan **plan);

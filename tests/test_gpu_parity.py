@@ -100,6 +100,88 @@ def test_generic_kernel_mixed_derivative_sweeps(evr, dcache, monkeypatch):
     assert rel_l2(part.apply_host(psi), oracle_apply(op2, psi, iG_range=(3, 17))) < TOL
 
 
+@pytest.mark.parametrize("nb0,B", [(1, 24), (2, 19)])
+def test_terms_larger_than_shared_memory(evr, nb0, B, monkeypatch):
+    """A Smolyak term whose work buffers exceed the 227 KB of shared memory (25^3 = 15 625 points; 20^3 x 2 channels) runs
+    in the generic kernel's global-buffer class -- the reference has no term-size limit (heap RDP arrays,
+    sub_module_basis_BtoG_GtoB_SG4.f90:2385-2581).  Curvilinear operator (cached mixed-derivative sweeps: three buffers),
+    constant-KEO operator, a term range, a block of vectors, the deterministic mode and a one-CTA scratch budget."""
+    basis = evr.workloads.hm_sg4_basis(3, 3, 3, 1, [B, B, B], nb0=nb0)
+    assert basis.tab_nq_OF_SRep.max() * nb0 * 16 > 227 * 1024
+    op = evr.workloads.synthetic_curvilinear(basis)
+    assert op.info(evr.lib.INFO_PATH) == 0
+    _check(op, 3)
+    psi = random_psi(basis.nb * nb0, 1, 4)
+    big = int(np.argmax(basis.tab_nq_OF_SRep))
+    part = evr.workloads.synthetic_curvilinear(basis, iG_range=(big, big + 2))
+    assert rel_l2(part.apply_host(psi), oracle_apply(op, psi, iG_range=(big, big + 2))) < TOL
+    rng = np.random.default_rng(3)
+    V = rng.standard_normal((basis.nqq, nb0, nb0))
+    hh = evr.ParamOp(basis, 1, evr.workloads.constant_keo_opgrids(3, nb0, np.ones(3), np.asfortranarray(V)))
+    _check(hh, 2)
+    monkeypatch.setenv("EVR_SG4_SCRATCH_MB", "1")
+    monkeypatch.setenv("EVR_SG4_DETERMINISTIC", "1")
+    det = evr.workloads.synthetic_curvilinear(basis)
+    a = det.apply_host(psi)
+    assert rel_l2(a, oracle_apply(op, psi)) < TOL
+    assert np.array_equal(a, det.apply_host(psi))
+
+
+def test_fast_path_plan_with_a_generic_remainder(evr):
+    """A constant-KEO plan stays on the fast path when a few of its terms are beyond the register tiles (mode of 17 > 16
+    points, as in HH 12-D at L = 8) or beyond the shared memory of an SM: those terms run in the generic kernel on the
+    caller's vectors, after the fast part.  Also the scaled action (sub_scaledOpPsi) and a block of vectors."""
+    import torch
+    basis, op = evr.workloads.henon_heiles(4, 8)                  # modes of 1 .. 17 points
+    assert op.info(evr.lib.INFO_PATH) == 1
+    rest = op.info(evr.lib.INFO_GENERIC_TERMS)
+    assert 0 < rest < basis.nb_SG // 4
+    out, ref = _check(op, 3)
+    psi = random_psi(basis.nb, 3, 12345)
+    E0, Esc = 0.7, 1.9
+    d_psi = torch.from_numpy(psi).cuda(); d_out = torch.empty_like(d_psi)
+    op.apply_device_scaled_ptr(3, d_psi.data_ptr(), d_out.data_ptr(), E0, Esc, torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert rel_l2(d_out.cpu().numpy(), (ref - E0 * psi) / Esc) < TOL
+    # block-ordered internal vector + remainder
+    import os
+    os.environ["EVR_SG4_BLOCK_ORDER"] = "1"
+    try:
+        _, op_b = evr.workloads.henon_heiles(4, 8)
+    finally:
+        del os.environ["EVR_SG4_BLOCK_ORDER"]
+    assert op_b.info(evr.lib.INFO_GENERIC_TERMS) == rest
+    assert rel_l2(op_b.apply_host(psi), ref) < TOL
+    op_b.apply_device_scaled_ptr(3, d_psi.data_ptr(), d_out.data_ptr(), E0, Esc, torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert rel_l2(d_out.cpu().numpy(), (ref - E0 * psi) / Esc) < TOL
+    # two channels, pool-based flavour: modes of 1, 9, 17 points
+    b2 = evr.workloads.hm_sg4_basis(3, 2, 2, 1, [8, 8, 8], nb0=2)     # sizes 1, 9, 17: the 17s go to the generic kernel
+    rng = np.random.default_rng(8)
+    V = np.asfortranarray(rng.standard_normal((b2.nqq, 2, 2)))
+    op2 = evr.ParamOp(b2, 1, evr.workloads.constant_keo_opgrids(3, 2, np.ones(3), V))
+    assert op2.info(evr.lib.INFO_PATH) == 1 and op2.info(evr.lib.INFO_GENERIC_TERMS) == 3
+    _check(op2, 2)
+
+
+def test_host_block_of_long_vectors_is_pipelined_per_vector(evr):
+    """evr_sg4_apply on a block of long vectors (>= 1 MB each) overlaps the copies of the neighbouring vectors with the
+    kernels of the current one (three streams); the result must equal the one-vector calls, from pageable and from
+    page-locked buffers."""
+    import torch
+    basis, op = evr.workloads.henon_heiles(12, 6)
+    assert basis.nb * 8 >= 1 << 20
+    psi = random_psi(basis.nb, 3, 21)
+    ref = oracle_apply(op, psi, nthreads=8)
+    out = op.apply_host(psi)
+    for v in range(3):
+        assert rel_l2(out[v], ref[v]) < TOL
+        assert rel_l2(op.apply_host(psi[v]), ref[v]) < TOL
+    pin_in = torch.from_numpy(psi).pin_memory(); pin_out = torch.empty_like(pin_in).pin_memory()
+    op.apply_host(pin_in.numpy(), out=pin_out.numpy())
+    assert rel_l2(pin_out.numpy(), ref) < TOL
+
+
 def test_type_op_0_scalar_operator(evr):
     basis = evr.workloads.hm_sg4_basis(4, 3, 3, 1, 2, nb0=2)
     rng = np.random.default_rng(5)

@@ -54,7 +54,7 @@ def test_oracle_gtob_inverts_btog_on_the_basis_space(evr):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("shape", ["hno3_lb2_lg4_x51", "hno3_lb3_lg5_x81", "hcn_lb6_lg7", "two_channels", "hh12d_L4"])
+@pytest.mark.parametrize("shape", ["hno3_lb2_lg4_x51", "hno3_lb3_lg5_x81", "hcn_lb6_lg7", "two_channels", "hh12d_L4", "beyond_smem"])
 def test_gpu_whole_vector_routines_match_oracle(shape, evr):
     rng = np.random.default_rng(11)
     if shape == "hno3_lb2_lg4_x51":
@@ -65,6 +65,9 @@ def test_gpu_whole_vector_routines_match_oracle(shape, evr):
         basis, nvec = evr.workloads.hm_sg4_basis(3, 6, 7, [10, 1, 1], [10, 2, 2]), 4
     elif shape == "two_channels":
         basis, nvec = evr.workloads.hm_sg4_basis(4, 3, 3, 1, 2, nb0=2), 3
+    elif shape == "beyond_smem":                         # 20^3 points x 2 channels: work buffers in global memory
+        basis, nvec = evr.workloads.hm_sg4_basis(3, 3, 3, 1, [19, 19, 19], nb0=2), 2
+        assert basis.tab_nq_OF_SRep.max() * 2 * 16 > 227 * 1024
     else:
         basis, nvec = evr.workloads.hm_sg4_basis(12, 4, 4, 1, 2), 2
     tr = evr.SG4Transforms(basis)
