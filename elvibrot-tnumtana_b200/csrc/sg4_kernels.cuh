@@ -87,20 +87,15 @@ template <bool BIG> __device__ __forceinline__ int mdivT(const int q, const unsi
     return mdiv(q, mg);
 }
 
-// ---- sum_b M[b*ms] * x[b*xs] with four independent partial sums: a single accumulator makes every multiply-add wait for
-// the previous one (the products of the large modes, n = 20 ... 80, are chains of n dependent DFMAs per output)
-__device__ __forceinline__ double dot4(const double *__restrict__ M, const int ms, const double *x, const int xs, const int n)
+// ---- sum_b M[b*ms] * x[b*xs]: one accumulator.  Four independent partial sums (to break the chain of n dependent DFMAs of
+// the large modes) were measured and are SLOWER: 268 vs 216 us for the 27-vector HCN block, 223 vs 190 us for HNO3 LB6/LG7
+// (profiles/r2/sweep20_generic_dot4.txt) -- the extra registers spill at the kernel's 64-register bound and the loop is
+// bound by its two memory instructions per multiply-add, not by the DFMA latency.
+__device__ __forceinline__ double dot_strided(const double *__restrict__ M, const int ms, const double *x, const int xs, const int n)
 {
-    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-    int b = 0;
-    for (; b + 3 < n; b += 4) {
-        s0 = fma(__ldg(M + (b + 0) * ms), x[(b + 0) * xs], s0);
-        s1 = fma(__ldg(M + (b + 1) * ms), x[(b + 1) * xs], s1);
-        s2 = fma(__ldg(M + (b + 2) * ms), x[(b + 2) * xs], s2);
-        s3 = fma(__ldg(M + (b + 3) * ms), x[(b + 3) * xs], s3);
-    }
-    for (; b < n; ++b) s0 = fma(__ldg(M + b * ms), x[b * xs], s0);
-    return n < 4 ? s0 : (s0 + s1) + (s2 + s3);
+    double s = 0.0;
+    for (int b = 0; b < n; ++b) s = fma(__ldg(M + b * ms), x[b * xs], s);
+    return s;
 }
 
 // ---- generic one-mode product through shared memory ----------------------------------
@@ -118,7 +113,7 @@ __device__ __forceinline__ void mode_product(const double *__restrict__ M, int n
         const int r = o - c * lo;
         const int q = mdivT<BIG>(r, mg_left);
         const int a = r - q * left;
-        out[o] = dot4(M + q, n_out, in + a + left * n_in * c, left, n_in);
+        out[o] = dot_strided(M + q, n_out, in + a + left * n_in * c, left, n_in);
     }
 }
 
@@ -207,8 +202,11 @@ __device__ __forceinline__ void mode_product_any(const double *__restrict__ M, i
 // BIG = true: the class of terms that do not fit in shared memory (no such limit in the reference): the two or three work
 // buffers of a CTA live in its slice of Cc.scratch (global memory, L2-resident for all but enormous terms) and the index
 // divisions are exact for any term size; everything else is the same code.
+#ifndef EVR_GEN_MINBLOCKS
+#define EVR_GEN_MINBLOCKS 4
+#endif
 template <bool BIG>
-static __global__ void __launch_bounds__(256, 4)
+static __global__ void __launch_bounds__(256, EVR_GEN_MINBLOCKS)
 sg4_term_kernel_generic(const PlanDev P, const GenClassDev Cc, const int npsi,
                         const double *__restrict__ psi, double *__restrict__ Hpsi)
 {
@@ -341,7 +339,7 @@ sg4_term_kernel_generic(const PlanDev P, const GenClassDev Cc, const int npsi,
                         const int qk = qd - mdivT<BIG>(qd, s_mgn[k]) * n;
                         const int base = q - qk * st;
 #pragma unroll
-                        for (int j = 0; j < EVR_MAXCH; ++j) if (j < nb0) d[j] = dot4(M + qk, n, cur + j * nq + base, st, n);
+                        for (int j = 0; j < EVR_MAXCH; ++j) if (j < nb0) d[j] = dot_strided(M + qk, n, cur + j * nq + base, st, n);
                     } else {
                         const double *Ma = P.D1 + s_oG[m1], *Mb = P.D1 + s_oG[m2];
                         const int na = s_tnq[m1], sa = s_str[m1], nbb = s_tnq[m2], sb = s_str[m2];
@@ -352,7 +350,7 @@ sg4_term_kernel_generic(const PlanDev P, const GenClassDev Cc, const int npsi,
                         for (int j = 0; j < EVR_MAXCH; ++j) if (j < nb0) {
                             double s = 0.0;
                             for (int b2 = 0; b2 < nbb; ++b2) {
-                                const double s1 = dot4(Ma + qa, na, cur + j * nq + base + b2 * sb, sa, na);
+                                const double s1 = dot_strided(Ma + qa, na, cur + j * nq + base + b2 * sb, sa, na);
                                 s = fma(__ldg(Mb + qb + nbb * b2), s1, s);
                             }
                             d[j] = s;
@@ -376,7 +374,7 @@ sg4_term_kernel_generic(const PlanDev P, const GenClassDev Cc, const int npsi,
                         const int j = mdivT<BIG>(o, s_mgq[D]), q = o - j * nq;
                         const int qda = mdivT<BIG>(q, s_mgq[a]);
                         const int qa = qda - mdivT<BIG>(qda, s_mgn[a]) * na;
-                        bufC[o] = dot4(Ma + qa, na, cur + j * nq + (q - qa * sa), sa, na);
+                        bufC[o] = dot_strided(Ma + qa, na, cur + j * nq + (q - qa * sa), sa, na);
                     }
                     __syncthreads();
                     const int t0 = P.sweep_begin[sw], t1 = P.sweep_begin[sw + 1];
@@ -397,7 +395,7 @@ sg4_term_kernel_generic(const PlanDev P, const GenClassDev Cc, const int npsi,
                                 const int qb = qdb - mdivT<BIG>(qdb, s_mgn[m2]) * nbb;
                                 const int base = q - qb * sb;
 #pragma unroll
-                                for (int j = 0; j < EVR_MAXCH; ++j) if (j < nb0) d[j] = dot4(Mb + qb, nbb, bufC + j * nq + base, sb, nbb);
+                                for (int j = 0; j < EVR_MAXCH; ++j) if (j < nb0) d[j] = dot_strided(Mb + qb, nbb, bufC + j * nq + base, sb, nbb);
                             }
                             add_term(t, d, acc, q);
                         }
@@ -568,7 +566,7 @@ sg4_term_kernel_type10(const PlanDev P, const Op10Dev O, const int npsi,
             const int qd = mdiv(q, s_mgs[k]);                        // no integer division per point
             const int qk = qd - mdiv(qd, s_mgn[k]) * nk;
             const int base = q - qk * st;
-            return dot4(M + qk, nk, arr + base, st, nk);
+            return dot_strided(M + qk, nk, arr + base, st, nk);
         };
         for (int c = 0; c < nb0; ++c) {
             // phi = psi_c * sq  -> chi buffer

@@ -50,6 +50,7 @@ class TermParallelOp:
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self._local = local_apply or self._cuda_apply
         self._symm = {}            # data_ptr -> (tensor, symmetric-memory handle, ctypes array of peer pointers)
+        self._flags = {}           # data_ptr -> [flag tensor, handle, peer pointers of the flags, calls made]
         self.collective = "torch.distributed.all_reduce"
 
     def symmetric_empty(self, *shape):
@@ -98,6 +99,29 @@ class TermParallelOp:
         ptrs = (C.c_void_p * self.world)(*[int(p) for p in hdl.buffer_ptrs])
         self._symm[t.data_ptr()] = (t, hdl, ptrs)
         self.collective = "evr_sg4_allreduce_slices (NVLink peer memory, reduce-scatter + all-gather in one kernel)"
+        # EVR_SG4_ALLREDUCE=fused: the all-reduce with in-kernel barriers (evr_sg4_allreduce_fused; flag words in one more
+        # peer-mapped buffer).  Measured equal to the kernel between two symmetric-memory barriers (37-38 us per 11 MB vector
+        # on 2 B200, NCCL 46 us; profiles/r2/allreduce_in_kernel_barriers.txt), so the latter stays the default.
+        if os.environ.get("EVR_SG4_ALLREDUCE", "p2p") == "fused":
+            fok, ft, fh = 0, None, None
+            try:
+                ft = symm_mem.empty(_lib.FLAG_WORDS, dtype=torch.int64, device=dev)
+                ft.zero_()
+                fok = 1
+            except Exception as e:      # noqa: BLE001
+                self._symm_error = repr(e)
+            if agree(fok):
+                try:
+                    fh = symm_mem.rendezvous(ft, self.group if self.group is not None else dist.group.WORLD)
+                    fok = 1 if int(fh.buffer_ptrs[self.rank]) == ft.data_ptr() else 0
+                except Exception as e:  # noqa: BLE001
+                    self._symm_error = repr(e)
+                    fok = 0
+                torch.cuda.synchronize()
+                if agree(fok):          # (also orders every rank's zero-fill before any peer's first signal)
+                    fptrs = (C.c_void_p * self.world)(*[int(p) for p in fh.buffer_ptrs])
+                    self._flags[t.data_ptr()] = [ft, fh, fptrs, 0]
+                    self.collective = "evr_sg4_allreduce_fused (NVLink peer memory; both cross-rank barriers inside the kernel)"
         return t
 
     def all_reduce(self, out):
@@ -111,6 +135,13 @@ class TermParallelOp:
             return out
         import torch
         _, hdl, ptrs = ent
+        fl = self._flags.get(out.data_ptr())
+        if fl is not None:          # barriers inside the kernel
+            fl[3] += 1
+            _lib.check(_lib.lib().evr_sg4_allreduce_fused(ptrs, fl[2], self.world, self.rank, out.numel(), fl[3],
+                                                          C.c_void_p(torch.cuda.current_stream().cuda_stream)),
+                       "evr_sg4_allreduce_fused")
+            return out
         hdl.barrier(channel=0)      # every rank's partial sum is complete (stream-ordered, device-side)
         _lib.check(_lib.lib().evr_sg4_allreduce_slices(ptrs, self.world, self.rank, out.numel(),
                                                        C.c_void_p(torch.cuda.current_stream().cuda_stream)),

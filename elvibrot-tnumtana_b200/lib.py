@@ -18,6 +18,7 @@ _lib = None
 TAB_NB_SG, TAB_NB, TAB_S, TAB_NQ, TAB_COUNT0, TAB_LMIN = 0, 1, 2, 3, 4, 5
 TAB_TAB_L, TAB_WEIGHT, TAB_TAB_NQ, TAB_TAB_NB, TAB_SUM_NQ, TAB_SUM_NB, TAB_PACKEDB, TAB_MAP = 10, 11, 12, 13, 14, 15, 16, 17
 INFO_LAUNCHES, INFO_ALG_BYTES_NPSI1, INFO_ALG_BYTES_PER_RHS_EXTRA, INFO_NQ_LOCAL, INFO_S_LOCAL = 0, 1, 2, 3, 4
+FLAG_WORDS = 2 * 16 + 2      # EVR_SG4_FLAG_WORDS (include/evr_sg4_comm.h)
 INFO_SMEM_BYTES, INFO_GRID_CTAS, INFO_PATH, INFO_FLOPS_NPSI1, INFO_ISO, INFO_DEVICES, INFO_GENERIC_TERMS = 5, 6, 7, 8, 9, 10, 11
 
 EXPORTS = [
@@ -27,7 +28,7 @@ EXPORTS = [
     "evr_sg4_plan_create", "evr_sg4_plan_create_ex", "evr_sg4_device_count", "evr_sg4_plan_set_op", "evr_sg4_plan_set_op10", "evr_sg4_apply", "evr_sg4_apply_device", "evr_sg4_apply_device_scaled",
     "evr_sg4_plan_info", "evr_sg4_plan_destroy", "evr_sg4_model_grid",
     "evr_sg4_BtoG", "evr_sg4_GtoB", "evr_sg4_DerivOp_G", "evr_sg4_BtoG_device", "evr_sg4_GtoB_device", "evr_sg4_DerivOp_G_device",
-    "evr_sg4_allreduce_slices", "evr_sg4_allgather_slices", "evr_sg4_reduce_slice", "evr_sg4_reduce_to", "evr_sg4_slice_bounds",
+    "evr_sg4_allreduce_slices", "evr_sg4_allreduce_fused", "evr_sg4_allgather_slices", "evr_sg4_reduce_slice", "evr_sg4_reduce_to", "evr_sg4_slice_bounds",
     "evr_sg4_set_devices", "evr_sg4_get_devices", "evr_sg4_host_register", "evr_sg4_host_unregister",
     "evr_sg4_vec_alloc", "evr_sg4_vec_free", "evr_sg4_vec_upload", "evr_sg4_vec_download", "evr_sg4_vec_gram", "evr_sg4_vec_lincomb",
     "evr_sg4_vec_scale", "evr_sg4_vec_precond", "evr_sg4_vec_schmidt",
@@ -104,6 +105,8 @@ def lib():
     L.evr_sg4_plan_destroy.argtypes = [C.POINTER(vp)]
     L.evr_sg4_allreduce_slices.restype = i32
     L.evr_sg4_allreduce_slices.argtypes = [vp, i32, i32, i64, vp]
+    L.evr_sg4_allreduce_fused.restype = i32
+    L.evr_sg4_allreduce_fused.argtypes = [vp, vp, i32, i32, i64, C.c_uint64, vp]
     L.evr_sg4_allgather_slices.restype = i32
     L.evr_sg4_allgather_slices.argtypes = [vp, i32, i32, i64, vp]
     L.evr_sg4_reduce_slice.restype = i32

@@ -21,6 +21,16 @@ extern "C" {
  * Returns 0, or non-zero with a message in evr_sg4_last_error(). */
 int evr_sg4_allreduce_slices(const void *const *peer_ptrs, int np, int rank, int64_t n, void *cuda_stream);
 
+/* The same all-reduce with the two cross-rank barriers INSIDE the kernel (no separate barrier launches): flag_ptrs[r] is
+ * rank r's flag array -- EVR_SG4_FLAG_WORDS 64-bit words of peer-mapped device memory, zero before the first call, used
+ * by nothing else -- and `call` is the number of this collective call on these buffers: 1, 2, 3, ... , the same on every
+ * rank.  Every rank must make the call (also with an empty slice).  When the kernel has ended on a rank, its buffer
+ * holds the full sum and no peer accesses it any more.  Replaces MPI_Reduce_sum_Bcast of Action_MPI_S1
+ * (sub_Operator/sub_OpPsi_SG4_MPI.f90:553-557). */
+#define EVR_SG4_FLAG_WORDS (2 * EVR_SG4_MAX_PEERS + 2)
+int evr_sg4_allreduce_fused(const void *const *peer_ptrs, const void *const *flag_ptrs, int np, int rank, int64_t n,
+                            uint64_t call, void *cuda_stream);
+
 /* The two halves separately, for callers whose input and output live in HOST memory (evr_sg4_apply with
  * evr_sg4_set_devices, bench.py e2e at N > 1): every rank copies only its slice of psi host -> device, the slices are
  * all-gathered over NVLink, and after the term kernels every rank reduces and returns only its slice of H psi, so that N

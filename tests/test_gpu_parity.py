@@ -502,6 +502,43 @@ def test_peer_memory_allreduce_kernel_single_device(evr, np_, n):
     assert evr.lib.lib().evr_sg4_allreduce_slices(ptrs, 0, 0, n, st) != 0      # bad arguments fail loudly
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("np_,n", [(2, 1001), (4, 4096), (8, 12345), (3, 2)])
+def test_allreduce_with_in_kernel_barriers_single_device(evr, np_, n):
+    """evr_sg4_allreduce_fused: the two cross-rank barriers are flag exchanges inside the kernel.  All "ranks" on one device,
+    one stream each (their small grids are co-resident, as the kernels of the real ranks are on their own devices); three
+    consecutive calls on the same buffers (call numbers 1, 2, 3) without any host synchronisation in between."""
+    import ctypes as C
+    import torch
+    torch.manual_seed(n)
+    W = evr.lib.FLAG_WORDS
+    bufs = [torch.randn(n, dtype=torch.float64, device="cuda") for _ in range(np_)]
+    flags = [torch.zeros(W, dtype=torch.int64, device="cuda") for _ in range(np_)]
+    streams = [torch.cuda.Stream() for _ in range(np_)]
+    torch.cuda.synchronize()
+    ptrs = (C.c_void_p * np_)(*[b.data_ptr() for b in bufs])
+    fptrs = (C.c_void_p * np_)(*[f.data_ptr() for f in flags])
+    want = bufs[0].clone()
+    for b in bufs[1:]:
+        want = want + b
+    for call in (1, 2, 3):
+        for r in range(np_):
+            evr.lib.check(evr.lib.lib().evr_sg4_allreduce_fused(ptrs, fptrs, np_, r, n, call, C.c_void_p(streams[r].cuda_stream)), "allreduce_fused")
+        if call == 1:
+            torch.cuda.synchronize()
+            for b in bufs:
+                assert torch.equal(b, want)
+    torch.cuda.synchronize()
+    for _ in range(2):                   # two more all-reduces of np identical vectors, summed in the kernel's order
+        acc = want.clone()
+        for _r in range(np_ - 1):
+            acc = acc + want
+        want = acc
+    for b in bufs:
+        assert torch.equal(b, want)
+    assert evr.lib.lib().evr_sg4_allreduce_fused(ptrs, fptrs, np_, 0, n, 0, None) != 0      # call number 0 is rejected
+
+
 # ---- the benchmarked configuration itself (BASELINE.json configs[4] at LB=LG=6 and 7, default plan settings):
 # block-ordered packed vector, batched work items of every size class, iso + pool-based instantiations side by side
 _BENCH_CACHE = {}
