@@ -169,7 +169,10 @@ int evr_sg4_plan_set_op10(evr_sg4_plan *plan, int n_act, const int32_t *act_mode
 /* H|psi> for npsi real right-hand sides (complex psi = 2 real RHS, sub_OpPsi.f90:392-407).
  * psi/Hpsi[ipsi*nb*nb0 + ib0*nb + iB]  (= Psi(ipsi)%RvecB).  Hpsi is overwritten
  * (the reference zeroes it, sub_OpPsi_SG4.f90:765); with a term sub-range it holds
- * this rank's partial sum (to be summed over ranks: MPI_Reduce_sum_Bcast / NCCL). */
+ * this rank's partial sum (to be summed over ranks: MPI_Reduce_sum_Bcast / NCCL).
+ * evr_sg4_apply on a block (npsi >= 2) of long vectors (>= 1 MB each) moves vector v+1 to the device and vector v-1 back
+ * while vector v is in the kernels; page-lock the buffers (evr_sg4_host_register) for the copies to overlap.
+ * There is no limit on the size of a Smolyak term: terms beyond the shared memory of an SM work in global buffers. */
 int evr_sg4_apply(evr_sg4_plan *plan, int npsi, const double *psi, double *Hpsi);          /* host buffers   */
 int evr_sg4_apply_device(evr_sg4_plan *plan, int npsi, const double *d_psi, double *d_Hpsi,
                          void *cuda_stream);
