@@ -55,7 +55,10 @@ static int upload(T **dptr, const T *h, size_t n)
 static int gen_class_of(int64_t tsize, int nb0)
 {
     if (tsize * nb0 * 2 * (int64_t)sizeof(double) > EVR_GEN_BIG_BYTES) return 0;
-    return tsize > 768 ? 1 : (tsize > 192 ? 2 : (tsize > 48 ? 3 : 4));
+    static const int th0 = getenv("EVR_SG4_GTH0") ? atoi(getenv("EVR_SG4_GTH0")) : 768;
+    static const int th1 = getenv("EVR_SG4_GTH1") ? atoi(getenv("EVR_SG4_GTH1")) : 192;
+    static const int th2 = getenv("EVR_SG4_GTH2") ? atoi(getenv("EVR_SG4_GTH2")) : 48;
+    return tsize > th0 ? 1 : (tsize > th1 ? 2 : (tsize > th2 ? 3 : 4));
 }
 // One set of generic-kernel launches: the size classes of either all terms of the plan (list == nullptr: contiguous
 // ranges of the work order) or of the terms listed by work-order index (the remainder of a fast-path plan).
