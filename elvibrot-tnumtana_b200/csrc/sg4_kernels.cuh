@@ -474,8 +474,10 @@ struct Op10Dev {
     int has_V;
     int nqmax;                   // largest term grid of the plan's range
     const double *V;             // [nb0*nb0][NQ_local]
-    const double *GG;            // [n_act*n_act][NQ_local]   GG[(j + n*i)*NQ + q] = GGiq(q,j,i)
+    const double *GG;            // [n_act*n_act][NQ_local]   GG[(j + n*i)*NQ + q] = GGiq(q,j,i); sym: [n(n+1)/2][NQ_local],
+                                 // component (min(i,j) + max(i,j)(max(i,j)+1)/2) -- the metric tensor is symmetric
     const double *Jac, *sq;      // [NQ_local]
+    int sym;                     // 1: GG stored as its upper triangle (plan set-up found GG(q,j,i) == GG(q,i,j) everywhere)
 };
 
 #define EVR_OP10_PTS 8           // grid points per thread kept in registers (nq <= 8*256)
@@ -581,8 +583,10 @@ sg4_term_kernel_type10(const PlanDev P, const Op10Dev O, const int npsi,
             for (int i = 0; i < n; ++i) {
                 for (int q = threadIdx.x; q < nq; q += blockDim.x) {
                     double s = 0.0;
-                    for (int j = 0; j < n; ++j)
-                        s = fma(__ldg(O.GG + (long long)(j + n * i) * P.NQ_local + T.grid_off + q), sR[(size_t)j * O.nqmax + q], s);
+                    for (int j = 0; j < n; ++j) {
+                        const int comp = O.sym ? (j <= i ? j + i * (i + 1) / 2 : i + j * (j + 1) / 2) : j + n * i;
+                        s = fma(__ldg(O.GG + (long long)comp * P.NQ_local + T.grid_off + q), sR[(size_t)j * O.nqmax + q], s);
+                    }
                     chi[q] = s * __ldg(Jq + q);
                 }
                 __syncthreads();

@@ -1054,7 +1054,23 @@ extern "C" int evr_sg4_plan_set_op10(evr_sg4_plan *p, int n_act, const int32_t *
             CUDA_TRY(cudaMemcpy(*d + (size_t)c * blk, h + (size_t)c * p->NQ_total + p->grid_start, (size_t)p->NQ_local * sizeof(double), cudaMemcpyHostToDevice));
         return 0;
     };
-    if (up_slice(&p->d_GG, GG, n_act * n_act)) return 1;
+    // the metric tensor is symmetric: when GG(q,j,i) == GG(q,i,j) holds exactly on this plan's grid range only the upper
+    // triangle is kept on the device (n(n+1)/2 + 2 instead of n^2 + 2 doubles per point)
+    bool sym = !(getenv("EVR_SG4_GG_FULL") && atoi(getenv("EVR_SG4_GG_FULL")) != 0);
+    for (int i = 0; i < n_act && sym; ++i)
+        for (int j = 0; j < i && sym; ++j) {
+            const double *a = GG + (size_t)(j + n_act * i) * p->NQ_total + p->grid_start, *b = GG + (size_t)(i + n_act * j) * p->NQ_total + p->grid_start;
+            if (std::memcmp(a, b, (size_t)p->NQ_local * sizeof(double)) != 0) sym = false;
+        }
+    O.sym = sym ? 1 : 0;
+    if (sym) {
+        if (p->d_GG) { cudaFree(p->d_GG); p->d_GG = nullptr; }
+        CUDA_TRY(cudaMalloc((void **)&p->d_GG, blk * (size_t)(n_act * (n_act + 1) / 2) * sizeof(double)));
+        for (int i = 0; i < n_act; ++i)
+            for (int j = 0; j <= i; ++j)
+                CUDA_TRY(cudaMemcpy(p->d_GG + (size_t)(j + i * (i + 1) / 2) * blk, GG + (size_t)(j + n_act * i) * p->NQ_total + p->grid_start,
+                                    (size_t)p->NQ_local * sizeof(double), cudaMemcpyHostToDevice));
+    } else if (up_slice(&p->d_GG, GG, n_act * n_act)) return 1;
     if (up_slice(&p->d_Jac, Jac, 1)) return 1;
     if (up_slice(&p->d_sq, sq, 1)) return 1;
     O.has_V = V ? 1 : 0;
@@ -1431,7 +1447,7 @@ extern "C" int64_t evr_sg4_plan_info(const evr_sg4_plan *p, int what)
     switch (what) {
     case EVR_INFO_LAUNCHES: return p->launches;
     case EVR_INFO_ALG_BYTES_NPSI1:
-        if (p->op10) return p->S_local * nb0 * 8 * 2 + p->S_local * 4 * 2 + p->NQ_local * 8 * (nb0 * nb0 * p->n_var + p->o10.n_act * p->o10.n_act + 2) + p->nb * nb0 * 8 * 2;
+        if (p->op10) return p->S_local * nb0 * 8 * 2 + p->S_local * 4 * 2 + p->NQ_local * 8 * (nb0 * nb0 * p->n_var + (p->o10.sym ? p->o10.n_act * (p->o10.n_act + 1) / 2 : p->o10.n_act * p->o10.n_act) + 2) + p->nb * nb0 * 8 * 2;
         return p->S_local * nb0 * 8 * 2 + p->S_local * 4 * 2 + p->NQ_local * nb0 * nb0 * 8 * p->n_var + p->nb * nb0 * 8 * 2;
     case EVR_INFO_ALG_BYTES_PER_RHS_EXTRA:
         return p->S_local * nb0 * 8 * 2 + p->nb * nb0 * 8 * 2;

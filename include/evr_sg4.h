@@ -162,7 +162,9 @@ int evr_sg4_model_grid(int model, int D, int nb_SG, int LG, const int32_t *tab_l
  * call (get_OpGrid_type10_OF_ONEDP_FOR_SG4, :2717-2728); here they are plan data, uploaded once.
  *   act_mode[j]  1-based SG4 mode owning active coordinate j (liste_QactTOQdyn + Tabder_Qdyn_TO_Qbasis)
  *   V            Grid(1:NQ,1:nb0,1:nb0) of the (0,0) term or NULL
- *   GG           GGiq(1:NQ,1:n_act,1:n_act), Jac(1:NQ), sqRhoOVERJac(1:NQ), whole Smolyak grid, column-major. */
+ *   GG           GGiq(1:NQ,1:n_act,1:n_act), Jac(1:NQ), sqRhoOVERJac(1:NQ), whole Smolyak grid, column-major.
+ * The device keeps only the upper triangle of GG (n_act(n_act+1)/2 + 2 doubles per point) when GG(q,j,i) == GG(q,i,j)
+ * holds exactly on the plan's grid range, the full tensor otherwise. */
 int evr_sg4_plan_set_op10(evr_sg4_plan *plan, int n_act, const int32_t *act_mode,
                           const double *V, const double *GG, const double *Jac, const double *sqRhoOVERJac);
 

@@ -278,6 +278,23 @@ def test_type_op_10_cached_metric(evr):
     out = op.apply_host(psi)
     for i in range(2):
         assert rel_l2(out[i], ref[i]) < TOL
+    # storage of the metric tensor: upper triangle when GG(q,j,i) == GG(q,i,j) exactly (n(n+1)/2 + 2 doubles per point instead
+    # of n^2 + 2), full otherwise -- the reference formula takes GG as given (sub_OpPsi_SG4.f90:1598-1618)
+    b5 = evr.workloads.hm_sg4_basis(5, 2, 4, 1, 1)
+    sym = evr.workloads.synthetic_type10(b5)
+    G = 0.5 * (sym.GG + sym.GG.transpose(0, 2, 1))
+    sym = evr.ParamOp10(b5, np.asfortranarray(G), sym.Jac, sym.sqRhoOVERJac, V=sym.V)
+    nq, n = b5.nqq, 5
+    sym_bytes = sym.info(evr.lib.INFO_ALG_BYTES_NPSI1)
+    G2 = G.copy(); G2[:, 0, 1] += 0.25                        # not symmetric any more
+    asym = evr.ParamOp10(b5, np.asfortranarray(G2), sym.Jac, sym.sqRhoOVERJac, V=sym.V)
+    assert asym.info(evr.lib.INFO_ALG_BYTES_NPSI1) - sym_bytes == nq * 8 * (n * n - n * (n + 1) // 2)
+    psi = random_psi(b5.nb, 2, 24)
+    for op in (sym, asym):
+        ref = oracle_apply10(op, psi)
+        out = op.apply_host(psi)
+        for i in range(2):
+            assert rel_l2(out[i], ref[i]) < TOL
 
 
 def test_gpu_pyrazine_autocorrelation_matches_reference(evr, golden):
