@@ -127,7 +127,7 @@ def main():
     ap.add_argument("--npsi", type=int, default=1)
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--partition", default="points", choices=["points", "count"],
+    ap.add_argument("--partition", default="points", choices=["points", "count", "cost"],
                     help="multi-GPU term ranges: equal grid points (default) or equal term counts (reference ini_iGs_MPI)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
@@ -187,6 +187,12 @@ def main():
     ops = evr.workloads.constant_keo_opgrids(args.D, 1, np.ones(args.D), V.reshape(-1, 1, 1))
     if args.partition == "count":
         lo_, hi_ = evr.distributed.ini_iGs(basis.nb_SG, world, rank)                 # reference ini_iGs_MPI
+    elif args.partition == "cost":
+        # equal modelled kernel time per rank: a term costs (1 + 0.15 * active modes) per grid point (gather / scatter /
+        # staging are per point, the transform passes grow with the number of modes of more than one point)
+        nact = (basis.nDind_SmolyakRep_Tab_nDval > 0).sum(axis=1)
+        cost = (basis.tab_nq_OF_SRep.astype(np.int64) * (20 + 3 * nact) // 20).astype(np.int32)
+        lo_, hi_ = evr.distributed.balanced_iGs(cost, world, rank)
     else:
         lo_, hi_ = evr.distributed.balanced_iGs(basis.tab_nq_OF_SRep, world, rank)   # equal grid points per rank
     op = evr.ParamOp(basis, 1, ops, iG_range=(lo_, hi_), device=local_rank)
@@ -248,7 +254,11 @@ def main():
     k_ms = sum(a.elapsed_time(b) for a, b in kev) / args.steps
     launches = op.info(evr.lib.INFO_LAUNCHES) - launches0
     t = torch.tensor([ms_total, k_ms], dtype=torch.float64, device="cuda")
+    k_ms_ranks = [k_ms]
     if world > 1:
+        every = [torch.zeros(1, dtype=torch.float64, device="cuda") for _ in range(world)]
+        dist.all_gather(every, t[1:2].clone())
+        k_ms_ranks = [float(e[0]) for e in every]
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_total, k_ms = float(t[0]), float(t[1])
     ms_step = ms_total / args.steps
@@ -355,7 +365,7 @@ def main():
                            "cache": "operator grid + mapping streamed per step (%.0f MB) > L2; no flush needed" % (alg1 / 1e6)
                            if alg1 > 130e6 else "inputs smaller than L2 (L2-warm numbers)",
                            "kernel_path": int(op.info(evr.lib.INFO_PATH)), "iso_flavour": int(op.info(evr.lib.INFO_ISO)), "setup_s": round(t_setup, 2)},
-                "e2e": e2e, "allreduce_ms": allreduce_ms, "allreduce_vs_nccl_rel_diff": allreduce_check,
+                "e2e": e2e, "allreduce_ms": allreduce_ms, "kernel_ms_per_rank": [round(x, 4) for x in k_ms_ranks], "allreduce_vs_nccl_rel_diff": allreduce_check,
                 "gpu_launches": int(launches) + (args.steps if (world > 1 and tp._symm) else 0), "roofline": roofline, "cpu_baseline": cpu, "parity": parity, "clocks": clocks}
         print(json.dumps(line))
         if parity is not None and not parity["ok"]:

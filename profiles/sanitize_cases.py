@@ -44,3 +44,38 @@ if which in ("all", "algebra"):
     v = torch.randn(5001, dtype=torch.float64).cuda()
     evr.algebra.schmidt(A[:0], v)
     print("algebra ran", float(G[0, 0]), flush=True)
+if which in ("all", "late"):
+    # kernels added late in round 2: global-buffer class of the generic and nested kernels (terms beyond shared memory),
+    # fast-path plan with a generic remainder (mode of 17 points), type_Op=10 with the triangular metric storage, the
+    # all-reduce with in-kernel barriers (3 "ranks" on streams of one device)
+    import ctypes as C
+    import torch
+    from helpers import oracle_apply10
+    big = evr.workloads.hm_sg4_basis(3, 3, 3, 1, [19, 19, 19], nb0=2)
+    check("20^3 x 2 channels (global work buffers, generic kernel)", evr.workloads.synthetic_curvilinear(big), 1)
+    tr = evr.SG4Transforms(big)
+    x = np.random.default_rng(0).standard_normal((1, big.nb * 2))
+    g = tr.RvecB_TO_RvecG(x); tr.RvecG_TO_RvecB(g); tr.DerivOp_TO_RvecG(g, 1, 3)
+    print("nested transforms with global work buffers ran", flush=True)
+    basis, op = evr.workloads.henon_heiles(4, 8)
+    assert op.info(evr.lib.INFO_PATH) == 1 and op.info(evr.lib.INFO_GENERIC_TERMS) > 0
+    check("HH 4-D L=8 (fast path + generic remainder)", op, 2)
+    b5 = evr.workloads.hm_sg4_basis(5, 2, 4, 1, 1)
+    o10 = evr.workloads.synthetic_type10(b5)
+    o10 = evr.ParamOp10(b5, np.asfortranarray(0.5 * (o10.GG + o10.GG.transpose(0, 2, 1))), o10.Jac, o10.sqRhoOVERJac, V=o10.V)
+    psi = random_psi(b5.nb, 1)
+    err = rel_l2(o10.apply_host(psi), oracle_apply10(o10, psi))
+    print(f"type_Op=10, triangular metric storage: rel L2 vs oracle {err:.2e}", flush=True)
+    assert err < 1e-12
+    np_, n = 3, 1001
+    bufs = [torch.randn(n, dtype=torch.float64, device="cuda") for _ in range(np_)]
+    flags = [torch.zeros(evr.lib.FLAG_WORDS, dtype=torch.int64, device="cuda") for _ in range(np_)]
+    streams = [torch.cuda.Stream() for _ in range(np_)]
+    want = bufs[0] + bufs[1] + bufs[2]
+    torch.cuda.synchronize()
+    ptrs = (C.c_void_p * np_)(*[b.data_ptr() for b in bufs]); fptrs = (C.c_void_p * np_)(*[f.data_ptr() for f in flags])
+    for r in range(np_):
+        evr.lib.check(evr.lib.lib().evr_sg4_allreduce_fused(ptrs, fptrs, np_, r, n, 1, C.c_void_p(streams[r].cuda_stream)), "fused")
+    torch.cuda.synchronize()
+    assert all(torch.equal(b, want) for b in bufs)
+    print("all-reduce with in-kernel barriers ran", flush=True)
