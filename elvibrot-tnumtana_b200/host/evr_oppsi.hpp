@@ -35,6 +35,8 @@ struct param_Op {
     int symab = -1;
     bool cplx = false;
     long long nb_OpPsi = 0;                       // counter bumped by sub_OpPsi (sub_OpPsi.f90:258)
+    bool Op_Transfo = false;                      // para_ReadOp%Op_Transfo / E0_Transfo (sub_OpPsi.f90:768-775)
+    double E0_Transfo = 0.0;
 };
 
 inline void check(int rc, const char *where)
@@ -82,20 +84,33 @@ inline void sub_OpPsi(const param_psi &Psi, param_psi &OpPsi, param_Op &para_Op)
     OpPsi.symab = Psi.symab;
 }
 
-inline void sub_TabOpPsi(const std::vector<param_psi> &TabPsi, std::vector<param_psi> &TabOpPsi, param_Op &para_Op)
-{
-    bool any_cplx = false;
-    for (const auto &p : TabPsi) any_cplx = any_cplx || p.cplx;
-    if (!any_cplx) { para_Op.nb_OpPsi += (long long)TabPsi.size(); sub_TabOpPsi_FOR_SGtype4(TabPsi, TabOpPsi, para_Op); return; }
-    TabOpPsi.assign(TabPsi.size(), param_psi());
-    for (size_t i = 0; i < TabPsi.size(); ++i) sub_OpPsi(TabPsi[i], TabOpPsi[i], para_Op);
-}
-
 // OpPsi <- (OpPsi - E0 Psi)/Esc
 inline void sub_scaledOpPsi(const param_psi &Psi, param_psi &OpPsi, double E0, double Esc)
 {
     if (Psi.cplx) for (size_t i = 0; i < Psi.CvecB.size(); ++i) OpPsi.CvecB[i] = (OpPsi.CvecB[i] - E0 * Psi.CvecB[i]) / Esc;
     else for (size_t i = 0; i < Psi.RvecB.size(); ++i) OpPsi.RvecB[i] = (OpPsi.RvecB[i] - E0 * Psi.RvecB[i]) / Esc;
+}
+
+// TransfoOp with para_Op%para_ReadOp%Op_Transfo: OpPsi = (H - E0_Transfo)(H - E0_Transfo) Psi, vector by vector (:768-775)
+inline void sub_TabOpPsi(const std::vector<param_psi> &TabPsi, std::vector<param_psi> &TabOpPsi, param_Op &para_Op,
+                         bool TransfoOp = false)
+{
+    if (TransfoOp && para_Op.Op_Transfo) {
+        TabOpPsi.assign(TabPsi.size(), param_psi());
+        for (size_t i = 0; i < TabPsi.size(); ++i) {
+            param_psi tmp;
+            sub_OpPsi(TabPsi[i], tmp, para_Op);
+            sub_scaledOpPsi(TabPsi[i], tmp, para_Op.E0_Transfo, 1.0);
+            sub_OpPsi(tmp, TabOpPsi[i], para_Op);
+            sub_scaledOpPsi(tmp, TabOpPsi[i], para_Op.E0_Transfo, 1.0);
+        }
+        return;
+    }
+    bool any_cplx = false;
+    for (const auto &p : TabPsi) any_cplx = any_cplx || p.cplx;
+    if (!any_cplx) { para_Op.nb_OpPsi += (long long)TabPsi.size(); sub_TabOpPsi_FOR_SGtype4(TabPsi, TabOpPsi, para_Op); return; }
+    TabOpPsi.assign(TabPsi.size(), param_psi());
+    for (size_t i = 0; i < TabPsi.size(); ++i) sub_OpPsi(TabPsi[i], TabOpPsi[i], para_Op);
 }
 
 } // namespace evr

@@ -232,6 +232,9 @@ class ParamOp:
         # Tabder_Qdyn_TO_Qbasis flattened: active coordinate i (1-based) lives in SG4 mode mode_of_Qact[i-1]
         self.mode_of_Qact = list(range(1, D + 1)) if mode_of_Qact is None else list(mode_of_Qact)
         self.iG_range = (0, BasisnD.nb_SG) if iG_range is None else tuple(iG_range)
+        # para_ReadOp%Op_Transfo / E0_Transfo (sub_OpPsi.f90:768-775): with TransfoOp the action is (H - E0)^2
+        self.Op_Transfo = False
+        self.E0_Transfo = 0.0
         self._plan = C.c_void_p()
         self._keep = []
 
@@ -393,9 +396,22 @@ def sub_TabOpPsi_FOR_SGtype4(Psi: List[ParamPsi], OpPsi: List[ParamPsi], para_Op
         OpPsi.append(ParamPsi(RvecB=y[i].copy(), cplx=False, symab=p.symab))
 
 
-def sub_TabOpPsi(TabPsi: List[ParamPsi], TabOpPsi: List[ParamPsi], para_Op: ParamOp):
+def sub_TabOpPsi(TabPsi: List[ParamPsi], TabOpPsi: List[ParamPsi], para_Op: ParamOp, TransfoOp: bool = False):
     """sub_OpPsi.f90:701 -> sub_PrimTabOpPsi :797 (SG4 branch :873-879). Real psi only, like the
-    reference's SG4 branch; complex vectors go one by one through sub_OpPsi."""
+    reference's SG4 branch; complex vectors go one by one through sub_OpPsi.
+    ``TransfoOp`` with ``para_Op.Op_Transfo`` (:768-775): OpPsi = (H - E0_Transfo)(H - E0_Transfo) Psi, vector by vector --
+    two actions, each followed by sub_scaledOpPsi(.., E0_Transfo, ONE)."""
+    if TransfoOp and para_Op.Op_Transfo:
+        out = []
+        for p in TabPsi:
+            tmp, o = ParamPsi(), ParamPsi()
+            sub_OpPsi(p, tmp, para_Op)
+            sub_scaledOpPsi(p, tmp, para_Op.E0_Transfo, 1.0)
+            sub_OpPsi(tmp, o, para_Op)
+            sub_scaledOpPsi(tmp, o, para_Op.E0_Transfo, 1.0)
+            out.append(o)
+        TabOpPsi[:] = out
+        return
     if any(p.cplx for p in TabPsi):
         out = []
         for p in TabPsi:

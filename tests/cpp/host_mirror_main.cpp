@@ -60,12 +60,21 @@ int main(int argc, char **argv)
         int stops = 0;
         try { std::vector<evr::param_psi> e, o; evr::sub_TabOpPsi_FOR_SGtype4(e, o, H); } catch (const evr::Stop &) { ++stops; }
         try { std::vector<evr::param_psi> e(1), o; e[0].cplx = true; evr::sub_TabOpPsi_FOR_SGtype4(e, o, H); } catch (const evr::Stop &) { ++stops; }
+        const long long n_OpPsi = H.nb_OpPsi;
+        // Op_Transfo / TransfoOp branch of sub_TabOpPsi (sub_OpPsi.f90:768-775): (H - E0)(H - E0) of the first real vector
+        std::vector<evr::param_psi> T2;
+        if (npsi) {
+            H.Op_Transfo = true; H.E0_Transfo = 0.37;
+            std::vector<evr::param_psi> one(1, Tab[0]);
+            evr::sub_TabOpPsi(one, T2, H, true);
+        }
         FILE *g = fopen(argv[2], "wb");
         long long cnt = stops; fwrite(&cnt, sizeof(cnt), 1, g);
-        cnt = H.nb_OpPsi; fwrite(&cnt, sizeof(cnt), 1, g);
+        cnt = n_OpPsi; fwrite(&cnt, sizeof(cnt), 1, g);
         if (ndev > 1 && evr_sg4_plan_info(H.plan, EVR_INFO_DEVICES) != ndev) { fprintf(stderr, "plan does not span %d devices\n", ndev); return 4; }
         for (int i = 0; i < npsi; ++i) fwrite(TabH[i].RvecB.data(), sizeof(double), n, g);
         for (int i = 0; i < ncplx; ++i) fwrite(CH[i].CvecB.data(), sizeof(double), 2 * n, g);
+        if (npsi) fwrite(T2[0].RvecB.data(), sizeof(double), n, g);
         fclose(g);
         evr_sg4_plan_destroy(&H.plan);
     } catch (const evr::Stop &e) {

@@ -51,6 +51,20 @@ def test_pyrazine_two_states_complex_psi(evr):
     assert rel_l2(Hpsi.CvecB.real, ref[0]) < TOL and rel_l2(Hpsi.CvecB.imag, ref[1]) < TOL
     basis2, op2 = evr.workloads.pyrazine_12d(2)
     _check(op2, 2)
+    # Op_Transfo / TransfoOp branch of sub_TabOpPsi (sub_OpPsi.f90:768-775): (H - E0)(H - E0) psi, complex and real vectors
+    op.Op_Transfo, op.E0_Transfo = True, 0.37
+    r = rng.standard_normal(n)
+    out = []
+    evr.sub_TabOpPsi([psi, evr.ParamPsi.real(r)], out, op, TransfoOp=True)
+    def twice(v):
+        h1 = oracle_apply(op, v[None, :])[0] - 0.37 * v
+        return oracle_apply(op, h1[None, :])[0] - 0.37 * h1
+    assert out[0].cplx and not out[1].cplx
+    assert rel_l2(out[0].CvecB.real, twice(c.real)) < TOL and rel_l2(out[0].CvecB.imag, twice(c.imag)) < TOL
+    assert rel_l2(out[1].RvecB, twice(r)) < TOL
+    plain = []
+    evr.sub_TabOpPsi([evr.ParamPsi.real(r)], plain, op)                 # TransfoOp absent: the plain action
+    assert rel_l2(plain[0].RvecB, oracle_apply(op, r[None, :])[0]) < TOL
 
 
 def test_hcn_shape_curvilinear(evr):
@@ -357,7 +371,11 @@ def test_cpp_host_mirror(evr, tmp_path, ndev):
     assert count == npsi + ncplx            # nb_OpPsi bookkeeping
     out = np.frombuffer(raw[16:], dtype=np.float64)
     Hr = out[: npsi * n].reshape(npsi, n)
-    Hc = out[npsi * n:].reshape(ncplx, n, 2)
+    Hc = out[npsi * n: npsi * n + 2 * ncplx * n].reshape(ncplx, n, 2)
+    T2 = out[npsi * n + 2 * ncplx * n:]
+    assert T2.size == n
+    h1 = oracle_apply(op, psi[:1])[0] - 0.37 * psi[0]
+    assert rel_l2(T2, oracle_apply(op, h1[None, :])[0] - 0.37 * h1) < TOL        # TransfoOp: (H - E0)^2 psi
     ref_r = oracle_apply(op, psi)
     ref_c = oracle_apply(op, np.concatenate([cpsi.real, cpsi.imag]))
     for i in range(npsi):
