@@ -480,8 +480,6 @@ struct Op10Dev {
     int sym;                     // 1: GG stored as its upper triangle (plan set-up found GG(q,j,i) == GG(q,i,j) everywhere)
 };
 
-#define EVR_OP10_PTS 8           // grid points per thread kept in registers (nq <= 8*256)
-
 // dynamic smem: bufA[cap] | bufB[cap] | R[n_act][nqmax] | chi[nqmax] | ints (as the generic kernel)
 static __global__ void __launch_bounds__(256)
 sg4_term_kernel_type10(const PlanDev P, const Op10Dev O, const int npsi,

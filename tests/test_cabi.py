@@ -54,3 +54,21 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h", ".f90")):
                 txt = open(os.path.join(dirpath, f), errors="replace").read()
                 assert "oracle" not in txt.lower().replace("no oracle", ""), f"{f} mentions the oracle"
+
+
+def test_python_constants_match_the_headers(evr):
+    """Enumerators and macros that elvibrot-tnumtana_b200/lib.py restates must equal include/*.h."""
+    import os
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    h = open(os.path.join(root, "include", "evr_sg4.h")).read()
+    enums = {m.group(1): int(m.group(2)) for m in re.finditer(r"\b(EVR_(?:INFO|TAB)_[A-Z0-9_]+)\s*=\s*(\d+)", h)}
+    assert enums, "no enumerators found in include/evr_sg4.h"
+    for name, value in enums.items():
+        py = name[len("EVR_"):]
+        assert hasattr(evr.lib, py), f"lib.py lacks {py}"
+        assert getattr(evr.lib, py) == value, (name, value, getattr(evr.lib, py))
+    c = open(os.path.join(root, "include", "evr_sg4_comm.h")).read()
+    peers = int(re.search(r"#define\s+EVR_SG4_MAX_PEERS\s+(\d+)", c).group(1))
+    assert re.search(r"#define\s+EVR_SG4_FLAG_WORDS\s+\(2 \* EVR_SG4_MAX_PEERS \+ 2\)", c)
+    assert evr.lib.FLAG_WORDS == 2 * peers + 2
