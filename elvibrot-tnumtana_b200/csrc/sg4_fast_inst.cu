@@ -56,6 +56,35 @@ int fast_launch(int mm, bool rt, bool tri, int nctas, int nthr, size_t smem, cud
     return fast_launch_0p(nctas, nthr, smem, st, P, C, npsi, psi, Hpsi);
 }
 
+// default (EVR_SG4_PERMUTE=0 restores the kernels above + a separate zero-fill): the zero-fill of the result rides on the
+// permute-in kernel, and the read-out gathers through the inverse permutation so that its stores are the coalesced side
+static __global__ void sg4_permute_in_zero(const int32_t *__restrict__ perm, const long long nb, const int nvecs,
+                                    const double *__restrict__ src, double *__restrict__ dst, double *__restrict__ zero)
+{
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nb; i += (long long)gridDim.x * blockDim.x) {
+        const int r = __ldg(perm + i);
+        for (int v = 0; v < nvecs; ++v) { dst[v * nb + i] = __ldg(src + v * nb + r); zero[v * nb + i] = 0.0; }
+    }
+}
+static __global__ void sg4_permute_out_inv(const int32_t *__restrict__ inv_perm, const long long nb, const int nvecs,
+                                    const double *__restrict__ src, double *__restrict__ dst)
+{
+    for (long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x; j < nb; j += (long long)gridDim.x * blockDim.x) {
+        const int i = __ldg(inv_perm + j);
+        for (int v = 0; v < nvecs; ++v) dst[v * nb + j] = src[v * nb + i];
+    }
+}
+int fast_permute_x(bool in, const int32_t *perm_or_inv, long long nb, int nvecs, const double *src, double *dst, double *zero, cudaStream_t st)
+{
+    const int thr = 256;
+    long long blocks = (nb + thr - 1) / thr;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    if (blocks < 1) blocks = 1;
+    if (in) sg4_permute_in_zero<<<(int)blocks, thr, 0, st>>>(perm_or_inv, nb, nvecs, src, dst, zero);
+    else sg4_permute_out_inv<<<(int)blocks, thr, 0, st>>>(perm_or_inv, nb, nvecs, src, dst);
+    return 0;
+}
+
 int fast_permute(bool in, const int32_t *perm, long long nb, int nvecs, const double *src, double *dst, cudaStream_t st)
 {
     const int thr = 256;

@@ -84,6 +84,7 @@ int fast_set_attributes();
 int fast_launch(int mm, bool rt, bool tri, int nctas, int nthr, size_t smem, cudaStream_t st,
                 const FastPlanDev &P, const FastClassDev &C, int npsi, const double *psi, double *Hpsi);
 int fast_permute(bool in, const int32_t *perm, long long nb, int nvecs, const double *src, double *dst, cudaStream_t st);
+int fast_permute_x(bool in, const int32_t *perm_or_inv, long long nb, int nvecs, const double *src, double *dst, double *zero, cudaStream_t st);
 // iso flavour: one [B|BTw|T] block per mode size n = 2..EVR_ISO_NMAX at compile-time offsets of a __constant__ array
 #define EVR_ISO_NMAX 15
 __host__ __device__ constexpr int iso_off(int n) { int o = 0; for (int m = 2; m < n; ++m) o += 3 * m * m; return o; }

@@ -882,6 +882,11 @@ static int build_fast_path(evr_sg4_plan *p, int nb_Term, const int32_t *term_mod
     cudaFree(p->d_fpos); p->d_fpos = nullptr; cudaFree(p->d_perm); p->d_perm = nullptr;
     if (upload(&p->d_fpos, fpos.data(), fpos.size())) return 1;
     if (upload(&p->d_perm, perm.data(), perm.size())) return 1;
+    cudaFree(p->d_inv_perm); p->d_inv_perm = nullptr;
+    // zero-fill of the result inside the permute-in kernel, read-out gathering through the inverse permutation (coalesced
+    // stores): 0.3480 vs 0.3507 ms at L = 7 (profiles/r2/sweep21_phase_isolation_and_latency.txt, sweep 31); EVR_SG4_PERMUTE=0: separate
+    // zero-fill, scattering read-out
+    if (block_order && !(getenv("EVR_SG4_PERMUTE") && atoi(getenv("EVR_SG4_PERMUTE")) == 0) && upload(&p->d_inv_perm, inv_perm.data(), inv_perm.size())) return 1;
     if (upload(&p->d_fmats, pool.data(), pool.size())) return 1;
     if (Vgrid && upload(&p->d_fV, fV.data(), fV.size())) return 1;
     evr::FastPlanDev &f = p->fpd;
@@ -1155,7 +1160,8 @@ static int launch_direct(evr_sg4_plan *p, int npsi, const double *d_psi_user, do
             CUDA_TRY(cudaMalloc((void **)&p->d_Hpsi_int, bytes));
             p->int_cap = nvecs * p->nb;
         }
-        evr::fast_permute(true, p->d_perm, p->nb, (int)nvecs, d_psi_user, p->d_psi_int, st);
+        if (p->d_inv_perm && !p->deterministic) evr::fast_permute_x(true, p->d_perm, p->nb, (int)nvecs, d_psi_user, p->d_psi_int, p->d_Hpsi_int, st);
+        else evr::fast_permute(true, p->d_perm, p->nb, (int)nvecs, d_psi_user, p->d_psi_int, st);
         p->launches += 1;
         d_psi = p->d_psi_int; d_Hpsi = p->d_Hpsi_int;
     }
@@ -1171,7 +1177,8 @@ static int launch_direct(evr_sg4_plan *p, int npsi, const double *d_psi_user, do
     }
     p->fpd.stage = det ? p->d_stage : nullptr; p->fpd.stage_ld = p->stage_ld;
     p->pd.stage = det ? p->d_stage : nullptr;  p->pd.stage_ld = p->stage_ld;
-    CUDA_TRY(cudaMemsetAsync(d_Hpsi, 0, bytes, st));                 // reference zeroes OpPsi (:765)
+    if (!(use_int && p->d_inv_perm && !p->deterministic))
+        CUDA_TRY(cudaMemsetAsync(d_Hpsi, 0, bytes, st));             // reference zeroes OpPsi (:765)
     if (p->n_terms > 0) {
         if (p->fast) {
             if ((long long)p->n_fitems * npsi > INT_MAX) return fail("evr_sg4_apply: n_terms * npsi exceeds 2^31 work items");
@@ -1226,7 +1233,8 @@ static int launch_direct(evr_sg4_plan *p, int npsi, const double *d_psi_user, do
             const int thr = 256;
             const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>((p->nb + thr - 1) / thr, 148 * 16));
             evr::sg4_permute_out_scaled<<<blocks, thr, 0, st>>>(p->d_perm, p->nb, (int)nvecs, sc.E0, sc.Esc, d_psi_user, p->d_Hpsi_int, d_Hpsi_user);
-        } else evr::fast_permute(false, p->d_perm, p->nb, (int)nvecs, p->d_Hpsi_int, d_Hpsi_user, st);
+        } else if (p->d_inv_perm) evr::fast_permute_x(false, p->d_inv_perm, p->nb, (int)nvecs, p->d_Hpsi_int, d_Hpsi_user, nullptr, st);
+        else evr::fast_permute(false, p->d_perm, p->nb, (int)nvecs, p->d_Hpsi_int, d_Hpsi_user, st);
         p->launches += 1;
         CUDA_TRY(cudaGetLastError());
     }
@@ -1478,7 +1486,7 @@ extern "C" int evr_sg4_plan_destroy(evr_sg4_plan **pp)
     cudaFree(p->d_fterms); cudaFree(p->d_fmap); cudaFree(p->d_fmats); cudaFree(p->d_fV);
     cudaFree(p->d_fpos); cudaFree(p->d_gmap); cudaFree(p->d_perm); cudaFree(p->d_psi_int); cudaFree(p->d_Hpsi_int);
     cudaFree(p->d_GG); cudaFree(p->d_Jac); cudaFree(p->d_sq);
-    cudaFree(p->d_det_off); cudaFree(p->d_det_ent); cudaFree(p->d_stage); cudaFree(p->d_fcounters); cudaFree(p->d_gscratch); cudaFree(p->d_nscratch); cudaFree(p->d_rscratch); cudaFree(p->d_rlist);
+    cudaFree(p->d_det_off); cudaFree(p->d_det_ent); cudaFree(p->d_stage); cudaFree(p->d_fcounters); cudaFree(p->d_gscratch); cudaFree(p->d_nscratch); cudaFree(p->d_rscratch); cudaFree(p->d_rlist); cudaFree(p->d_inv_perm);
     if (p->s_in) { cudaStreamDestroy(p->s_in); cudaStreamDestroy(p->s_out); cudaEventDestroy(p->ev_pin); cudaEventDestroy(p->ev_pout); }
     if (p->stream) cudaStreamDestroy(p->stream);
     for (int c = 0; c < EVR_MAX_FCLASSES; ++c) { if (p->side[c]) cudaStreamDestroy(p->side[c]); if (p->ev_join[c]) cudaEventDestroy(p->ev_join[c]); }

@@ -38,6 +38,7 @@ struct evr_sg4_plan {
     int32_t *d_gmap = nullptr;           // per term: internal packed index in term-local (internal layout) order
     uint16_t *d_fpos = nullptr;          // per term: term-local position of each sorted entry
     int32_t *d_perm = nullptr;           // internal packed order -> reference packed index (0-based)
+    int32_t *d_inv_perm = nullptr;       // the inverse (read-out with coalesced stores; nullptr with EVR_SG4_PERMUTE=0)
     double *d_psi_int = nullptr, *d_Hpsi_int = nullptr;   // packed vectors in the internal (block) order
     int64_t int_cap = 0;
     double *d_fmats = nullptr, *d_fV = nullptr;
