@@ -31,6 +31,9 @@
 !              its own slice of tab_iB_OF_SRep_TO_iB (evr_sg4_plan_create_ex).
 ! Errors     : non-zero status -> message + STOP (the reference's behaviour).
 !
+! Kinds      : the reference's default build (makefile INT = 4, Rkind = real64): its integer tables and Rkind arrays are
+!              passed to the C-ABI as int32_t / double without a copy; an INT=8 build fails at the explicit interfaces.
+!
 ! NOT COMPILED IN THIS REPOSITORY'S CI: the build image has no Fortran
 ! compiler (SURVEY.md F2).  The flattening below follows the reference's type
 ! definitions (file:line cited inline); INTEGRATION.md lists the makefile lines
